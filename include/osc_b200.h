@@ -1,0 +1,182 @@
+/*
+ * include/osc_b200.h -- C-ABI of the B200 batched operational-space controller.
+ *
+ * Drop-in boundary for ONE hot path of vannem95/operational-space-control: the
+ * per-step control law  OSCData + TaskspaceTargets + contact mask -> QP -> torques.
+ * The reference has no FFI of its own; its "operator API" is the C++ class
+ * OperationalSpaceController (one per robot directory).  Each entry point below
+ * names the reference code it replaces (paths relative to the reference's
+ * operational-space-control/ directory, walter_sr lines; the wheels and go2
+ * headers hold the same code at the offsets listed in SURVEY.md 8a).
+ *
+ * Plain C: pointers and sizes only, no torch / Eigen / abseil types.
+ * All matrices are FP64, row-major and contiguous per environment, exactly
+ * the memory layout of the reference's OSCData fields (containers.h:13-21):
+ *   M       [n_envs][nv*nv]      osc_data.mass_matrix        (:436-438)
+ *   C       [n_envs][nv]         osc_data.coriolis_matrix    (:441-442)
+ *   J       [n_envs][6*ns*nv]    osc_data.taskspace_jacobian (:485-487)  rows [Jp(all sites); Jr(all sites)]
+ *   bias    [n_envs][6*ns]       osc_data.taskspace_bias     (:491-492)
+ *   targets [n_envs][ns*6]       TaskspaceTargets            (aliases.h:21)
+ *   mask    [n_envs][nc]         State.contact_mask          (containers.h:41), 0.0 / 1.0
+ * osc_data.contact_jacobian is not an input: it is rows [3ns-3nc, 3ns) of J
+ * transposed (:497-503) and is read from J on the device.
+ *
+ * Thread-safety: one caller per handle.  Multi-GPU: one handle per device.
+ * There is NO CPU fallback: every call fails with OSC_ERR_CUDA when the
+ * device or the kernels are unavailable.
+ */
+#ifndef OSC_B200_H
+#define OSC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSC_MAX_SITES 32
+#define OSC_MAX_NU 16
+
+enum {
+  OSC_OK = 0,
+  OSC_ERR_INVALID = -1,     /* bad argument / unsupported robot shape */
+  OSC_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
+  OSC_ERR_STATE = -3,       /* call order violated (step before setup, ...) */
+  OSC_ERR_ALLOC = -4
+};
+
+/* per-environment solver status, OSQP's values (osqp/include/constants.h) */
+enum {
+  OSC_SOLVED = 1,
+  OSC_SOLVED_INACCURATE = 2,
+  OSC_MAX_ITER_REACHED = -2,
+  OSC_UNSOLVED = -10
+};
+
+/* What the reference bakes in per robot at build time:
+ * autogen_defines.h sizes (<robot>/autogen/autogen.py:469-513), the YAML's
+ * weights_config / friction_coefficient (config/<robot>/ *.yaml, consumed by
+ * autogen.py:20-41,331-336) and the hard-coded bounds
+ * (operational_space_controller.h:282,309-353; go2 :285-308). */
+typedef struct {
+  int nv, nu, nc, ns;             /* model::nv_size, nu_size, contact_site_ids_size, site_ids_size */
+  double w_trans[OSC_MAX_SITES];  /* <site>_translational_tracking, site order = noncontact then contact */
+  double w_rot[OSC_MAX_SITES];    /* <site>_rotational_tracking */
+  double w_torque, w_reg;         /* torque, regularization */
+  double mu;                      /* friction_coefficient */
+  double u_lb[OSC_MAX_NU], u_ub[OSC_MAX_NU];
+  double fz_max;                  /* big_number */
+} osc_robot_spec;
+
+/* The subset of osqp::OsqpSettings that changes the iterates; same names and
+ * OSQP 0.6.3 defaults (the reference passes OsqpSettings() untouched,
+ * operational_space_controller.h:110).  adaptive_rho_interval = 0 resolves to
+ * 4 x check_termination (OSQP's rule without PROFILING); a PROFILING build
+ * picks it from wall-clock time, so pass it explicitly to mimic one. */
+typedef struct {
+  double rho, sigma, alpha;
+  double eps_abs, eps_rel;
+  double adaptive_rho_tolerance;
+  int scaling;
+  int adaptive_rho;
+  int adaptive_rho_interval;
+  int max_iter;
+  int check_termination;
+  int warm_start;
+} osc_settings;
+
+typedef struct osc_handle osc_handle;
+
+typedef struct {
+  /* device pointers of the handle's input buffers (layouts above) for callers
+   * whose data is already in HBM; write them on the stream passed to osc_step */
+  double *M, *C, *J, *bias, *targets, *mask;
+  /* device pointers of the outputs */
+  double *torque;   /* [n_envs][nu]   torque_command  (:631) */
+  double *solution; /* [n_envs][n]    solution        (:592) */
+  double *dual;     /* [n_envs][m]    dual_solution   (:593) */
+  int *iters;       /* [n_envs]       OSQP info->iter */
+  int *status;      /* [n_envs]       OSC_SOLVED ...  (exit_code, :591) */
+  double *pri_res, *dua_res, *rho; /* [n_envs] */
+} osc_device_buffers;
+
+/* OsqpSettings() defaults. */
+int osc_default_settings(osc_settings *s);
+
+/* Replaces the controller constructor + initialize()'s allocation
+ * (operational_space_controller.h:110-163) for n_envs environments on CUDA
+ * device `device`.  Only the reference's shapes are compiled:
+ * (nv,nu,nc,ns) = (14,8,8,17) [walter_sr, walter_sr_wheels], (18,12,4,5) [unitree_go2]. */
+int osc_create(const osc_robot_spec *spec, const osc_settings *settings, int n_envs, int device,
+               osc_handle **out);
+int osc_destroy(osc_handle *h);
+/* message of the last error on this handle (or of a failed osc_create when h == NULL) */
+const char *osc_last_error(const osc_handle *h);
+
+int osc_num_envs(const osc_handle *h);
+int osc_get_device_buffers(osc_handle *h, osc_device_buffers *out);
+
+/* Host AoS -> device (pinned staging + cudaMemcpyAsync on `stream`).  Replaces the
+ * six row->column-major copies of update_optimization_data (:517-522): no
+ * transposes are needed, the kernels read the reference's row-major layout.
+ * Any pointer may be NULL to leave that field unchanged. `stream` is a cudaStream_t. */
+int osc_upload(osc_handle *h, const double *M, const double *C, const double *J,
+               const double *bias, const double *targets, const double *mask, void *stream);
+
+/* set_up_optimization() for every environment (:355-392): first QP build and
+ * solver Init (cold iterates, rho = settings.rho).  Must precede osc_step. */
+int osc_setup(osc_handle *h, void *stream);
+
+/* One control_loop body after update_osc_data() for every environment:
+ * update_optimization_data (:515-539, CasADi H,f,Aeq,beq,Aineq,bineq),
+ * update_optimization (:541-587, bounds with contact mask, OSQP data update that
+ * keeps the warm start), solve_optimization (:589-594) and the torque slice (:631). */
+int osc_step(osc_handle *h, void *stream);
+
+/* reset_optimization() (:596-601): zero primal/dual warm start. */
+int osc_reset_warm_start(osc_handle *h, void *stream);
+
+/* Device -> host copies of the results of the last step (async on `stream`;
+ * call osc_sync before reading).  NULL pointers are skipped. */
+int osc_download(osc_handle *h, double *torque, double *solution, double *dual, int *iters,
+                 int *status, double *pri_res, double *dua_res, double *rho, void *stream);
+int osc_sync(osc_handle *h, void *stream);
+
+/* update_state/update_taskspace_targets + control step + get_torque_command for a
+ * whole batch with HOST buffers: upload, step, download torques, synchronise. */
+int osc_step_host(osc_handle *h, const double *M, const double *C, const double *J,
+                  const double *bias, const double *targets, const double *mask, double *torque,
+                  void *stream);
+
+/* Use caller-owned DEVICE memory as the inputs of subsequent osc_setup/osc_step calls
+ * (same layouts; NULL keeps the handle's own buffer for that field).  Lets a rollout
+ * loop or a benchmark keep several batches resident in HBM without copies. */
+int osc_bind_device_inputs(osc_handle *h, const double *M, const double *C, const double *J,
+                           const double *bias, const double *targets, const double *mask);
+
+/* Page-locked host memory for the caller's OSCData arrays, so osc_upload /
+ * osc_step_host copy at full PCIe rate without a staging pass. */
+int osc_host_alloc(size_t bytes, void **out);
+int osc_host_free(void *p);
+
+/* Per-kernel device timing: when enabled, every osc_step brackets its two kernels
+ * with CUDA events on the launch stream; osc_timing_read synchronises, returns the
+ * average milliseconds per step of each kernel since the last read, and resets. */
+typedef struct {
+  float build_ms, solve_ms;
+  int steps;
+} osc_kernel_times;
+int osc_timing_enable(osc_handle *h, int on);
+int osc_timing_read(osc_handle *h, osc_kernel_times *out);
+
+/* number of kernels launched by this handle so far (bench bookkeeping) */
+long long osc_kernel_launches(const osc_handle *h);
+
+/* FP64 FMA micro-benchmark used as the roofline denominator for the solver
+ * kernel: returns achieved TFLOP/s (2 flop per DFMA) on `device`. */
+int osc_measure_dfma_tflops(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

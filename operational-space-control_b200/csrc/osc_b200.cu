@@ -1,0 +1,704 @@
+// osc_b200.cu -- sm_100a kernels and the C-ABI (include/osc_b200.h) of the batched
+// operational-space controller.
+//
+// Kernels
+//   build_qp_kernel   K2: objective matrices H (dv block) and f from J, bias, targets.
+//                     HBM-bound stream: every environment's J/bias/targets record is
+//                     pulled into shared memory by 1-D TMA bulk copies (cp.async.bulk,
+//                     mbarrier completion) through a 3-stage ring; one thread per
+//                     output entry.
+//   init_state_kernel set_up_optimization(): cold iterates, rho0, first linear cost.
+//   solve_kernel      K3: one warp per environment, persistent CTAs with a dynamic
+//                     work counter.  Loads M, H, f, C, contact rows of J, mask and the
+//                     warm-start record with TMA bulk copies into the warp's private
+//                     shared-memory workspace, then runs osc::Core::step (scaling,
+//                     factorisation, ADMM, un-scaling) entirely on chip in FP64.
+//   reset_warm_kernel reset_optimization().
+//   dfma_peak_kernel  FP64-FMA roofline denominator.
+//
+// No CPU fallback exists in this library.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "osc_params.h"
+
+namespace osc {
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA unit, UBLKCP in SASS)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// K2: objective build
+// ---------------------------------------------------------------------------
+template <class D>
+struct BuildStage {
+  double J[D::S * D::NV];
+  double bias[D::S];
+  double targets[D::S];
+};
+constexpr int kBuildStages = 3;
+
+template <class D>
+constexpr int build_threads() {
+  return ((BuildQP<D>::NITEM + 31) / 32) * 32;
+}
+
+template <class D>
+__global__ void __launch_bounds__(build_threads<D>())
+build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
+                const double* __restrict__ bias, const double* __restrict__ targets,
+                double* __restrict__ Hdv, double* __restrict__ fdv, int n_envs) {
+  using B = BuildQP<D>;
+  constexpr int NV = D::NV, S = D::S;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BuildStage<D>* stages = reinterpret_cast<BuildStage<D>*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kBuildStages * sizeof(BuildStage<D>));
+  double* w_row = reinterpret_cast<double*>(bars + kBuildStages);
+
+  const int tid = threadIdx.x;
+  constexpr uint32_t kBytes = sizeof(BuildStage<D>);
+  auto issue = [&](int stage, int env) {
+    BuildStage<D>& st = stages[stage];
+    mbar_expect_tx(&bars[stage], kBytes);
+    bulk_g2s(st.J, J + (size_t)env * S * NV, sizeof(st.J), &bars[stage]);
+    bulk_g2s(st.bias, bias + (size_t)env * S, sizeof(st.bias), &bars[stage]);
+    bulk_g2s(st.targets, targets + (size_t)env * S, sizeof(st.targets), &bars[stage]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kBuildStages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  for (int k = tid; k < S; k += blockDim.x) w_row[k] = p.w_row[k];
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < kBuildStages; ++s) {
+      const int env = blockIdx.x + s * gridDim.x;
+      if (env < n_envs) issue(s, env);
+    }
+  }
+  // this thread's output entry
+  int a = 0, b = 0;
+  const bool is_h = tid < B::NPAIR, is_f = !is_h && tid < B::NITEM;
+  if (is_h) {
+    int t = tid;
+    while (t > a) {  // lower triangle, row by row
+      t -= a + 1;
+      ++a;
+    }
+    b = t;
+  } else if (is_f) {
+    a = tid - B::NPAIR;
+  }
+  int it = 0;
+  for (int env = blockIdx.x; env < n_envs; env += gridDim.x, ++it) {
+    const int stage = it % kBuildStages;
+    const uint32_t parity = (it / kBuildStages) & 1;
+    mbar_wait(&bars[stage], parity);
+    const BuildStage<D>& st = stages[stage];
+    if (is_h) {
+      const double v = B::h_entry(st.J, w_row, p.w_reg, a, b);
+      double* H = Hdv + (size_t)env * NV * NV;
+      H[a * NV + b] = v;
+      H[b * NV + a] = v;
+    } else if (is_f) {
+      fdv[(size_t)env * NV + a] = B::f_entry(st.J, st.bias, st.targets, w_row, a);
+    }
+    __syncthreads();  // everyone is done with this stage
+    if (tid == 0) {
+      const int next = env + kBuildStages * gridDim.x;
+      if (next < n_envs) issue(stage, next);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// set_up_optimization(): Init state
+// ---------------------------------------------------------------------------
+template <class D>
+__global__ void init_state_kernel(double* __restrict__ state, const double* __restrict__ fdv,
+                                  double rho0, int n_envs) {
+  constexpr int ST = D::STATE, QOFF = D::N + 2 * D::M;
+  const size_t total = (size_t)n_envs * ST;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int env = (int)(i / ST), k = (int)(i - (size_t)env * ST);
+    double v = 0.0;
+    if (k >= QOFF && k < QOFF + D::NV) v = fdv[(size_t)env * D::NV + (k - QOFF)];
+    else if (k == QOFF + D::NV) v = rho0;
+    else if (k == QOFF + D::NV + 1) v = 1.0;
+    state[i] = v;
+  }
+}
+
+template <class D>
+__global__ void reset_warm_kernel(double* __restrict__ state, int n_envs) {
+  constexpr int ST = D::STATE, QOFF = D::N + 2 * D::M;
+  const size_t total = (size_t)n_envs * QOFF;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int env = (int)(i / QOFF), k = (int)(i - (size_t)env * QOFF);
+    state[(size_t)env * ST + k] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: solve
+// ---------------------------------------------------------------------------
+struct SolveArgs {
+  const double *M, *C, *J, *mask, *Hdv, *fdv;
+  double* state;
+  double *torque, *sol_x, *sol_y, *pri_res, *dua_res, *rho;
+  int *iters, *status;
+  int* counter;
+  int n_envs;
+};
+
+template <class D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
+  using WS = Workspace<D>;
+  using C32 = Core<D, 32>;
+  constexpr int NV = D::NV;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WS* wsb = reinterpret_cast<WS*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WARPS * sizeof(WS));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WS& w = wsb[warp];
+  uint64_t* bar = &bars[warp];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  constexpr uint32_t kBytes =
+      sizeof(double) * (NV * NV + NV * NV + D::NZ * NV + D::STATE + NV + NV + D::NC);
+  for (;;) {
+    int env = 0;
+    if (lane == 0) env = atomicAdd(a.counter, 1);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= a.n_envs) break;
+    if (lane == 0) {
+      fence_proxy_async();  // order the previous environment's generic-proxy accesses
+      mbar_expect_tx(bar, kBytes);
+      bulk_g2s(w.Ae, a.M + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
+      bulk_g2s(w.Pdv, a.Hdv + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
+      bulk_g2s(w.scratch, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(double) * D::NZ * NV,
+               bar);
+      bulk_g2s(w.x, a.state + (size_t)env * D::STATE, sizeof(double) * D::STATE, bar);
+      bulk_g2s(w.Cv, a.C + (size_t)env * NV, sizeof(double) * NV, bar);
+      bulk_g2s(w.fv, a.fdv + (size_t)env * NV, sizeof(double) * NV, bar);
+      bulk_g2s(w.maskv, a.mask + (size_t)env * D::NC, sizeof(double) * D::NC, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const Result r = C32::step(w, p, lane, a.sol_x + (size_t)env * D::N,
+                               a.sol_y + (size_t)env * D::M, a.torque + (size_t)env * D::NU);
+    double* st = a.state + (size_t)env * D::STATE;
+    const double* ws = w.x;  // x z y qprev rho_flag are contiguous
+    for (int i = lane; i < D::STATE; i += 32) st[i] = ws[i];
+    if (lane == 0) {
+      a.iters[env] = r.iter;
+      a.status[env] = r.status;
+      a.pri_res[env] = r.pri_res;
+      a.dua_res[env] = r.dua_res;
+      a.rho[env] = r.rho;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 FMA peak
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4,
+         a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace osc
+
+// ===========================================================================
+// C-ABI
+// ===========================================================================
+struct osc_handle {
+  osc_robot_spec spec;
+  osc_settings settings;
+  osc::Params params;
+  osc::Shape shape;
+  int n_envs, device, sm_count;
+  bool setup_done;
+  // sizes per environment (doubles)
+  int nv, nu, nc, ns, n, m, s, state;
+  // device buffers
+  double *dM, *dC, *dJ, *dBias, *dTargets, *dMask;
+  double *dH, *dF, *dState;
+  double *dTorque, *dX, *dY, *dPri, *dDua, *dRho;
+  int *dIters, *dStatus, *dCounter;
+  // inputs actually read by the kernels (own buffers unless osc_bind_device_inputs)
+  const double *iM, *iC, *iJ, *iBias, *iTargets, *iMask;
+  // optional per-kernel timing
+  bool timing;
+  std::vector<cudaEvent_t> ev;  // 3 events per recorded step
+  size_t ev_used;
+  long long launches;
+  std::string err;
+};
+
+namespace {
+thread_local std::string g_create_err;
+
+#define OSC_CUDA(h, call)                                                         \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);              \
+      return OSC_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+template <class D>
+constexpr int solve_warps() {
+  // as many warps (environments) per CTA as fit in 227 KB of shared memory, capped
+  return (int)((227 * 1024 - 256) / sizeof(osc::Workspace<D>)) > 16
+             ? 16
+             : (int)((227 * 1024 - 256) / sizeof(osc::Workspace<D>));
+}
+
+template <class D>
+int launch_build(osc_handle* h, cudaStream_t st) {
+  constexpr int threads = osc::build_threads<D>();
+  const size_t smem = osc::kBuildStages * sizeof(osc::BuildStage<D>) +
+                      osc::kBuildStages * sizeof(uint64_t) + D::S * sizeof(double);
+  auto kern = osc::build_qp_kernel<D>;
+  OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  OSC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = h->sm_count * per_sm;
+  if (grid > h->n_envs) grid = h->n_envs;
+  kern<<<grid, threads, smem, st>>>(h->params, h->iJ, h->iBias, h->iTargets, h->dH, h->dF,
+                                    h->n_envs);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
+template <class D>
+int launch_init_state(osc_handle* h, cudaStream_t st) {
+  const int threads = 256;
+  const size_t total = (size_t)h->n_envs * D::STATE;
+  int grid = (int)((total + threads - 1) / threads);
+  if (grid > h->sm_count * 8) grid = h->sm_count * 8;
+  osc::init_state_kernel<D><<<grid, threads, 0, st>>>(h->dState, h->dF, h->params.rho0,
+                                                      h->n_envs);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
+template <class D>
+int launch_reset(osc_handle* h, cudaStream_t st) {
+  const int threads = 256;
+  const size_t total = (size_t)h->n_envs * (D::N + 2 * D::M);
+  int grid = (int)((total + threads - 1) / threads);
+  if (grid > h->sm_count * 8) grid = h->sm_count * 8;
+  osc::reset_warm_kernel<D><<<grid, threads, 0, st>>>(h->dState, h->n_envs);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
+template <class D>
+int launch_solve(osc_handle* h, cudaStream_t st) {
+  constexpr int WARPS = solve_warps<D>();
+  static_assert(WARPS >= 1, "workspace does not fit in shared memory");
+  const size_t smem = WARPS * sizeof(osc::Workspace<D>) + WARPS * sizeof(uint64_t);
+  auto kern = osc::solve_kernel<D, WARPS>;
+  OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = h->sm_count;
+  const int need = (h->n_envs + WARPS - 1) / WARPS;
+  if (grid > need) grid = need;
+  OSC_CUDA(h, cudaMemsetAsync(h->dCounter, 0, sizeof(int), st));
+  osc::SolveArgs a;
+  a.M = h->iM; a.C = h->iC; a.J = h->iJ; a.mask = h->iMask; a.Hdv = h->dH; a.fdv = h->dF;
+  a.state = h->dState;
+  a.torque = h->dTorque; a.sol_x = h->dX; a.sol_y = h->dY;
+  a.pri_res = h->dPri; a.dua_res = h->dDua; a.rho = h->dRho;
+  a.iters = h->dIters; a.status = h->dStatus; a.counter = h->dCounter; a.n_envs = h->n_envs;
+  kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
+#define OSC_DISPATCH(h, fn, ...)                                                    \
+  ((h)->shape == osc::Shape::kWalter ? fn<osc::WalterDims>(__VA_ARGS__)             \
+                                     : fn<osc::Go2Dims>(__VA_ARGS__))
+
+int check_handle(const osc_handle* h) { return h ? OSC_OK : OSC_ERR_INVALID; }
+}  // namespace
+
+extern "C" {
+
+int osc_default_settings(osc_settings* s) {
+  if (!s) return OSC_ERR_INVALID;
+  osc::default_settings(s);
+  return OSC_OK;
+}
+
+const char* osc_last_error(const osc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_envs, int device,
+               osc_handle** out) {
+  if (!spec || !out || n_envs <= 0) {
+    g_create_err = "osc_create: null argument or n_envs <= 0";
+    return OSC_ERR_INVALID;
+  }
+  *out = nullptr;
+  const osc::Shape shape = osc::shape_of(*spec);
+  if (shape == osc::Shape::kNone) {
+    g_create_err = "osc_create: unsupported robot shape (compiled: nv,nu,nc,ns = 14,8,8,17 | 18,12,4,5)";
+    return OSC_ERR_INVALID;
+  }
+  osc_settings st;
+  if (settings) st = *settings; else osc::default_settings(&st);
+  if (st.max_iter < 1 || st.check_termination < 0 || st.scaling < 0 || st.rho <= 0 ||
+      st.sigma <= 0 || st.alpha <= 0 || st.alpha >= 2) {
+    g_create_err = "osc_create: invalid settings";
+    return OSC_ERR_INVALID;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) {
+    g_create_err = std::string("osc_create: no usable CUDA device (") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") +
+                   "); this library has no CPU fallback";
+    return OSC_ERR_CUDA;
+  }
+  osc_handle* h = new (std::nothrow) osc_handle();
+  if (!h) return OSC_ERR_ALLOC;
+  h->spec = *spec;
+  h->settings = st;
+  h->params = osc::make_params(*spec, st);
+  h->shape = shape;
+  h->n_envs = n_envs;
+  h->device = device;
+  h->setup_done = false;
+  h->launches = 0;
+  h->nv = spec->nv; h->nu = spec->nu; h->nc = spec->nc; h->ns = spec->ns;
+  h->n = spec->nv + spec->nu + 3 * spec->nc;
+  h->m = spec->nv + 4 * spec->nc + h->n;
+  h->s = 6 * spec->ns;
+  h->state = shape == osc::Shape::kWalter ? osc::WalterDims::STATE : osc::Go2Dims::STATE;
+  auto fail = [&](cudaError_t ce, const char* what) {
+    g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
+    osc_destroy(h);
+    return ce == cudaErrorMemoryAllocation ? OSC_ERR_ALLOC : OSC_ERR_CUDA;
+  };
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail(ce, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(ce, "cudaGetDeviceProperties");
+  if (prop.major < 10) {
+    g_create_err = "osc_create: kernels are built for sm_100a only";
+    osc_destroy(h);
+    return OSC_ERR_CUDA;
+  }
+  h->sm_count = prop.multiProcessorCount;
+  const size_t N = (size_t)n_envs;
+  struct { double** p; size_t n; } bufs[] = {
+      {&h->dM, N * h->nv * h->nv}, {&h->dC, N * h->nv}, {&h->dJ, N * h->s * h->nv},
+      {&h->dBias, N * h->s}, {&h->dTargets, N * h->s}, {&h->dMask, N * h->nc},
+      {&h->dH, N * h->nv * h->nv}, {&h->dF, N * h->nv}, {&h->dState, N * h->state},
+      {&h->dTorque, N * h->nu}, {&h->dX, N * h->n}, {&h->dY, N * h->m},
+      {&h->dPri, N}, {&h->dDua, N}, {&h->dRho, N}};
+  for (auto& b : bufs) {
+    if ((ce = cudaMalloc((void**)b.p, b.n * sizeof(double))) != cudaSuccess) return fail(ce, "cudaMalloc");
+    if ((ce = cudaMemset(*b.p, 0, b.n * sizeof(double))) != cudaSuccess) return fail(ce, "cudaMemset");
+  }
+  if ((ce = cudaMalloc((void**)&h->dIters, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  if ((ce = cudaMalloc((void**)&h->dStatus, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  if ((ce = cudaMalloc((void**)&h->dCounter, sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  cudaMemset(h->dIters, 0, N * sizeof(int));
+  cudaMemset(h->dStatus, 0, N * sizeof(int));
+  h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
+  h->iMask = h->dMask;
+  h->timing = false;
+  h->ev_used = 0;
+  *out = h;
+  return OSC_OK;
+}
+
+int osc_destroy(osc_handle* h) {
+  if (!h) return OSC_ERR_INVALID;
+  cudaSetDevice(h->device);
+  double* d[] = {h->dM, h->dC, h->dJ, h->dBias, h->dTargets, h->dMask, h->dH, h->dF, h->dState,
+                 h->dTorque, h->dX, h->dY, h->dPri, h->dDua, h->dRho};
+  for (double* p : d) if (p) cudaFree(p);
+  if (h->dIters) cudaFree(h->dIters);
+  if (h->dStatus) cudaFree(h->dStatus);
+  if (h->dCounter) cudaFree(h->dCounter);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  delete h;
+  return OSC_OK;
+}
+
+int osc_num_envs(const osc_handle* h) { return h ? h->n_envs : OSC_ERR_INVALID; }
+
+int osc_get_device_buffers(osc_handle* h, osc_device_buffers* out) {
+  if (check_handle(h) || !out) return OSC_ERR_INVALID;
+  out->M = h->dM; out->C = h->dC; out->J = h->dJ; out->bias = h->dBias;
+  out->targets = h->dTargets; out->mask = h->dMask;
+  out->torque = h->dTorque; out->solution = h->dX; out->dual = h->dY;
+  out->iters = h->dIters; out->status = h->dStatus;
+  out->pri_res = h->dPri; out->dua_res = h->dDua; out->rho = h->dRho;
+  return OSC_OK;
+}
+
+int osc_upload(osc_handle* h, const double* M, const double* C, const double* J,
+               const double* bias, const double* targets, const double* mask, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  const size_t N = (size_t)h->n_envs, B = sizeof(double);
+  if (M) OSC_CUDA(h, cudaMemcpyAsync(h->dM, M, N * h->nv * h->nv * B, cudaMemcpyHostToDevice, st));
+  if (C) OSC_CUDA(h, cudaMemcpyAsync(h->dC, C, N * h->nv * B, cudaMemcpyHostToDevice, st));
+  if (J) OSC_CUDA(h, cudaMemcpyAsync(h->dJ, J, N * h->s * h->nv * B, cudaMemcpyHostToDevice, st));
+  if (bias) OSC_CUDA(h, cudaMemcpyAsync(h->dBias, bias, N * h->s * B, cudaMemcpyHostToDevice, st));
+  if (targets) OSC_CUDA(h, cudaMemcpyAsync(h->dTargets, targets, N * h->s * B, cudaMemcpyHostToDevice, st));
+  if (mask) OSC_CUDA(h, cudaMemcpyAsync(h->dMask, mask, N * h->nc * B, cudaMemcpyHostToDevice, st));
+  return OSC_OK;
+}
+
+int osc_setup(osc_handle* h, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  int rc = OSC_DISPATCH(h, launch_build, h, st);
+  if (rc) return rc;
+  rc = OSC_DISPATCH(h, launch_init_state, h, st);
+  if (rc) return rc;
+  h->setup_done = true;
+  return OSC_OK;
+}
+
+int osc_step(osc_handle* h, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!h->setup_done) {
+    h->err = "osc_step: osc_setup has not been called (set_up_optimization precedes control_loop)";
+    return OSC_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  cudaEvent_t* ev = nullptr;
+  if (h->timing) {
+    if (h->ev_used + 3 > h->ev.size()) {
+      for (int i = 0; i < 3; ++i) {
+        cudaEvent_t e;
+        OSC_CUDA(h, cudaEventCreate(&e));
+        h->ev.push_back(e);
+      }
+    }
+    ev = &h->ev[h->ev_used];
+    h->ev_used += 3;
+    OSC_CUDA(h, cudaEventRecord(ev[0], st));
+  }
+  int rc = OSC_DISPATCH(h, launch_build, h, st);
+  if (rc) return rc;
+  if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
+  rc = OSC_DISPATCH(h, launch_solve, h, st);
+  if (rc) return rc;
+  if (ev) OSC_CUDA(h, cudaEventRecord(ev[2], st));
+  return OSC_OK;
+}
+
+int osc_bind_device_inputs(osc_handle* h, const double* M, const double* C, const double* J,
+                           const double* bias, const double* targets, const double* mask) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  h->iM = M ? M : h->dM;
+  h->iC = C ? C : h->dC;
+  h->iJ = J ? J : h->dJ;
+  h->iBias = bias ? bias : h->dBias;
+  h->iTargets = targets ? targets : h->dTargets;
+  h->iMask = mask ? mask : h->dMask;
+  const uintptr_t all = (uintptr_t)h->iM | (uintptr_t)h->iC | (uintptr_t)h->iJ |
+                        (uintptr_t)h->iBias | (uintptr_t)h->iTargets | (uintptr_t)h->iMask;
+  if (all & 15) {
+    h->err = "osc_bind_device_inputs: device pointers must be 16-byte aligned (TMA bulk copies)";
+    h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
+    h->iMask = h->dMask;
+    return OSC_ERR_INVALID;
+  }
+  return OSC_OK;
+}
+
+int osc_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return OSC_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+    *out = nullptr;
+    return OSC_ERR_CUDA;
+  }
+  return OSC_OK;
+}
+int osc_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? OSC_OK : OSC_ERR_CUDA; }
+
+int osc_timing_enable(osc_handle* h, int on) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  h->timing = on != 0;
+  h->ev_used = 0;
+  return OSC_OK;
+}
+
+int osc_timing_read(osc_handle* h, osc_kernel_times* out) {
+  if (check_handle(h) || !out) return OSC_ERR_INVALID;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  double b = 0.0, s = 0.0;
+  const int steps = (int)(h->ev_used / 3);
+  for (int i = 0; i < steps; ++i) {
+    OSC_CUDA(h, cudaEventSynchronize(h->ev[3 * i + 2]));
+    float t0 = 0, t1 = 0;
+    OSC_CUDA(h, cudaEventElapsedTime(&t0, h->ev[3 * i], h->ev[3 * i + 1]));
+    OSC_CUDA(h, cudaEventElapsedTime(&t1, h->ev[3 * i + 1], h->ev[3 * i + 2]));
+    b += t0;
+    s += t1;
+  }
+  out->steps = steps;
+  out->build_ms = steps ? (float)(b / steps) : 0.f;
+  out->solve_ms = steps ? (float)(s / steps) : 0.f;
+  h->ev_used = 0;
+  return OSC_OK;
+}
+
+int osc_reset_warm_start(osc_handle* h, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!h->setup_done) {
+    h->err = "osc_reset_warm_start: osc_setup has not been called";
+    return OSC_ERR_STATE;
+  }
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  return OSC_DISPATCH(h, launch_reset, h, (cudaStream_t)stream);
+}
+
+int osc_download(osc_handle* h, double* torque, double* solution, double* dual, int* iters,
+                 int* status, double* pri_res, double* dua_res, double* rho, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  const size_t N = (size_t)h->n_envs, B = sizeof(double);
+  if (torque) OSC_CUDA(h, cudaMemcpyAsync(torque, h->dTorque, N * h->nu * B, cudaMemcpyDeviceToHost, st));
+  if (solution) OSC_CUDA(h, cudaMemcpyAsync(solution, h->dX, N * h->n * B, cudaMemcpyDeviceToHost, st));
+  if (dual) OSC_CUDA(h, cudaMemcpyAsync(dual, h->dY, N * h->m * B, cudaMemcpyDeviceToHost, st));
+  if (iters) OSC_CUDA(h, cudaMemcpyAsync(iters, h->dIters, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (status) OSC_CUDA(h, cudaMemcpyAsync(status, h->dStatus, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (pri_res) OSC_CUDA(h, cudaMemcpyAsync(pri_res, h->dPri, N * B, cudaMemcpyDeviceToHost, st));
+  if (dua_res) OSC_CUDA(h, cudaMemcpyAsync(dua_res, h->dDua, N * B, cudaMemcpyDeviceToHost, st));
+  if (rho) OSC_CUDA(h, cudaMemcpyAsync(rho, h->dRho, N * B, cudaMemcpyDeviceToHost, st));
+  return OSC_OK;
+}
+
+int osc_sync(osc_handle* h, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  OSC_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return OSC_OK;
+}
+
+int osc_step_host(osc_handle* h, const double* M, const double* C, const double* J,
+                  const double* bias, const double* targets, const double* mask, double* torque,
+                  void* stream) {
+  int rc = osc_upload(h, M, C, J, bias, targets, mask, stream);
+  if (rc) return rc;
+  if ((rc = osc_step(h, stream))) return rc;
+  if ((rc = osc_download(h, torque, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         stream)))
+    return rc;
+  return osc_sync(h, stream);
+}
+
+long long osc_kernel_launches(const osc_handle* h) { return h ? h->launches : 0; }
+
+int osc_measure_dfma_tflops(int device, double* tflops) {
+  if (!tflops) return OSC_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return OSC_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OSC_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(double) * blocks * threads) != cudaSuccess) return OSC_ERR_ALLOC;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    osc::dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0 + rep);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return OSC_ERR_CUDA; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return OSC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+"""ctypes binding of the product library `libosc_b200.so` (C-ABI: include/osc_b200.h)
+and `BatchedOSC`, the batched sibling of the reference's OperationalSpaceController.
+
+Loading fails loudly when the library is missing; every call fails with the
+library's error message when no B200 is present.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .specs import RobotSpec
+
+_PKG = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+LIB_PATH = os.path.join(_PKG, "libosc_b200.so")
+
+OSC_MAX_SITES = 32
+OSC_MAX_NU = 16
+
+SOLVED, SOLVED_INACCURATE, MAX_ITER_REACHED, UNSOLVED = 1, 2, -2, -10
+
+EXPORTS = (
+    "osc_default_settings", "osc_create", "osc_destroy", "osc_last_error", "osc_num_envs",
+    "osc_get_device_buffers", "osc_upload", "osc_setup", "osc_step", "osc_reset_warm_start",
+    "osc_download", "osc_sync", "osc_step_host", "osc_kernel_launches",
+    "osc_measure_dfma_tflops", "osc_host_alloc", "osc_host_free", "osc_bind_device_inputs",
+    "osc_timing_enable", "osc_timing_read",
+)
+
+
+class CRobotSpec(C.Structure):
+    _fields_ = [
+        ("nv", C.c_int), ("nu", C.c_int), ("nc", C.c_int), ("ns", C.c_int),
+        ("w_trans", C.c_double * OSC_MAX_SITES), ("w_rot", C.c_double * OSC_MAX_SITES),
+        ("w_torque", C.c_double), ("w_reg", C.c_double), ("mu", C.c_double),
+        ("u_lb", C.c_double * OSC_MAX_NU), ("u_ub", C.c_double * OSC_MAX_NU),
+        ("fz_max", C.c_double),
+    ]
+
+
+class CSettings(C.Structure):
+    """Same field names as osqp::OsqpSettings (the subset that changes iterates)."""
+    _fields_ = [
+        ("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+        ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("adaptive_rho_tolerance", C.c_double),
+        ("scaling", C.c_int), ("adaptive_rho", C.c_int), ("adaptive_rho_interval", C.c_int),
+        ("max_iter", C.c_int), ("check_termination", C.c_int), ("warm_start", C.c_int),
+    ]
+
+
+class CDeviceBuffers(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "M", "C", "J", "bias", "targets", "mask", "torque", "solution", "dual", "iters", "status",
+        "pri_res", "dua_res", "rho")]
+
+
+class CKernelTimes(C.Structure):
+    _fields_ = [("build_ms", C.c_float), ("solve_ms", C.c_float), ("steps", C.c_int)]
+
+
+class OscError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise OscError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                       "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    L.osc_default_settings.argtypes = [C.POINTER(CSettings)]
+    L.osc_create.argtypes = [C.POINTER(CRobotSpec), C.POINTER(CSettings), C.c_int, C.c_int,
+                             C.POINTER(vp)]
+    L.osc_destroy.argtypes = [vp]
+    L.osc_last_error.argtypes = [vp]
+    L.osc_last_error.restype = C.c_char_p
+    L.osc_num_envs.argtypes = [vp]
+    L.osc_get_device_buffers.argtypes = [vp, C.POINTER(CDeviceBuffers)]
+    L.osc_upload.argtypes = [vp] + [vp] * 6 + [vp]
+    L.osc_setup.argtypes = [vp, vp]
+    L.osc_step.argtypes = [vp, vp]
+    L.osc_reset_warm_start.argtypes = [vp, vp]
+    L.osc_download.argtypes = [vp] + [vp] * 8 + [vp]
+    L.osc_sync.argtypes = [vp, vp]
+    L.osc_step_host.argtypes = [vp] + [vp] * 7 + [vp]
+    L.osc_kernel_launches.argtypes = [vp]
+    L.osc_kernel_launches.restype = C.c_longlong
+    L.osc_measure_dfma_tflops.argtypes = [C.c_int, dp]
+    L.osc_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.osc_host_free.argtypes = [vp]
+    L.osc_bind_device_inputs.argtypes = [vp] + [vp] * 6
+    L.osc_timing_enable.argtypes = [vp, C.c_int]
+    L.osc_timing_read.argtypes = [vp, C.POINTER(CKernelTimes)]
+    _LIB = L
+    return L
+
+
+def default_settings(**kw) -> CSettings:
+    s = CSettings()
+    load().osc_default_settings(C.byref(s))
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise AttributeError(k)
+        setattr(s, k, v)
+    return s
+
+
+def c_spec(spec: RobotSpec) -> CRobotSpec:
+    r = CRobotSpec()
+    r.nv, r.nu, r.nc, r.ns = spec.nv, spec.nu, spec.nc, spec.ns
+    for i in range(spec.ns):
+        r.w_trans[i], r.w_rot[i] = spec.w_trans[i], spec.w_rot[i]
+    r.w_torque, r.w_reg, r.mu, r.fz_max = spec.w_torque, spec.w_reg, spec.mu, spec.fz_max
+    for i in range(spec.nu):
+        r.u_lb[i], r.u_ub[i] = spec.u_lb[i], spec.u_ub[i]
+    return r
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (osc_host_alloc)."""
+    L = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = L.osc_host_alloc(max(n, 16), C.byref(p))
+    if rc:
+        raise OscError(f"osc_host_alloc failed ({rc}): {L.osc_last_error(None).decode()}")
+    buf = (C.c_char * max(n, 16)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = (p, buf)
+    return arr
+
+
+_PINNED = {}
+
+_FIELDS = ("M", "C", "J", "bias", "targets", "mask")
+
+
+class BatchedOSC:
+    """N environments of one robot, one CUDA device.
+
+    Mirrors the reference controller's life cycle
+    (walter_sr/operational_space_controller.h:110-240):
+        initialize_optimization()      -> setup(inputs)
+        control_loop body              -> step(inputs)   (returns torques)
+        get_torque_command/get_solution-> torques() / solution() / dual_solution()
+    """
+
+    def __init__(self, spec: RobotSpec, n_envs: int, settings: CSettings | None = None,
+                 device: int = 0):
+        self.L = load()
+        self.spec, self.n_envs, self.device = spec, int(n_envs), device
+        self.settings = settings if settings is not None else default_settings()
+        self._cspec = c_spec(spec)
+        self.h = C.c_void_p()
+        rc = self.L.osc_create(C.byref(self._cspec), C.byref(self.settings), self.n_envs, device,
+                               C.byref(self.h))
+        if rc:
+            self.h = None
+            raise OscError(f"osc_create failed ({rc}): {self.L.osc_last_error(None).decode()}")
+
+    # -- helpers ---------------------------------------------------------
+    def _check(self, rc, what):
+        if rc:
+            raise OscError(f"{what} failed ({rc}): {self.L.osc_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.osc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shapes(self):
+        sp, N = self.spec, self.n_envs
+        return dict(M=(N, sp.nv, sp.nv), C=(N, sp.nv), J=(N, sp.s, sp.nv), bias=(N, sp.s),
+                    targets=(N, sp.ns, 6), mask=(N, sp.nc))
+
+    def _ptrs(self, inputs):
+        keep, ptrs = [], []
+        shapes = self._shapes()
+        for k in _FIELDS:
+            a = inputs.get(k) if inputs is not None else None
+            if a is None:
+                ptrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != shapes[k]:
+                raise ValueError(f"{k}: expected shape {shapes[k]}, got {a.shape}")
+            keep.append(a)
+            ptrs.append(a.ctypes.data)
+        return keep, ptrs
+
+    # -- API -------------------------------------------------------------
+    def upload(self, inputs, stream=None):
+        keep, ptrs = self._ptrs(inputs)
+        self._check(self.L.osc_upload(self.h, *ptrs, stream), "osc_upload")
+        self._check(self.L.osc_sync(self.h, stream), "osc_sync")  # host arrays may go away
+
+    def setup(self, inputs=None, stream=None):
+        if inputs is not None:
+            self.upload(inputs, stream)
+        self._check(self.L.osc_setup(self.h, stream), "osc_setup")
+
+    def step_device(self, stream=None):
+        """Control step on the inputs already resident in HBM (no host traffic)."""
+        self._check(self.L.osc_step(self.h, stream), "osc_step")
+
+    def step(self, inputs, stream=None) -> np.ndarray:
+        """Host buffers in, torques out (upload + step + download + sync)."""
+        keep, ptrs = self._ptrs(inputs)
+        tq = np.empty((self.n_envs, self.spec.nu))
+        self._check(self.L.osc_step_host(self.h, *ptrs, tq.ctypes.data, stream), "osc_step_host")
+        return tq
+
+    def step_host_into(self, ptrs, torque_out: np.ndarray, stream=None):
+        """Hot-loop variant of step(): pre-resolved input pointers, caller-owned output."""
+        self._check(self.L.osc_step_host(self.h, *ptrs, torque_out.ctypes.data, stream),
+                    "osc_step_host")
+
+    def reset_warm_start(self, stream=None):
+        self._check(self.L.osc_reset_warm_start(self.h, stream), "osc_reset_warm_start")
+
+    def sync(self, stream=None):
+        self._check(self.L.osc_sync(self.h, stream), "osc_sync")
+
+    def results(self, stream=None) -> dict:
+        sp, N = self.spec, self.n_envs
+        out = dict(torque=np.empty((N, sp.nu)), x=np.empty((N, sp.n)), y=np.empty((N, sp.m)),
+                   iters=np.empty(N, np.int32), status=np.empty(N, np.int32),
+                   pri_res=np.empty(N), dua_res=np.empty(N), rho=np.empty(N))
+        self._check(self.L.osc_download(
+            self.h, out["torque"].ctypes.data, out["x"].ctypes.data, out["y"].ctypes.data,
+            out["iters"].ctypes.data, out["status"].ctypes.data, out["pri_res"].ctypes.data,
+            out["dua_res"].ctypes.data, out["rho"].ctypes.data, stream), "osc_download")
+        self.sync(stream)
+        return out
+
+    def torques(self, stream=None) -> np.ndarray:
+        tq = np.empty((self.n_envs, self.spec.nu))
+        self._check(self.L.osc_download(self.h, tq.ctypes.data, None, None, None, None, None,
+                                        None, None, stream), "osc_download")
+        self.sync(stream)
+        return tq
+
+    def device_buffers(self) -> CDeviceBuffers:
+        b = CDeviceBuffers()
+        self._check(self.L.osc_get_device_buffers(self.h, C.byref(b)), "osc_get_device_buffers")
+        return b
+
+    def bind_device_inputs(self, M=None, C_=None, J=None, bias=None, targets=None, mask=None):
+        """Device pointers (ints) of caller-owned HBM buffers to read inputs from."""
+        self._check(self.L.osc_bind_device_inputs(self.h, M, C_, J, bias, targets, mask),
+                    "osc_bind_device_inputs")
+
+    def enable_timing(self, on: bool = True):
+        self._check(self.L.osc_timing_enable(self.h, int(on)), "osc_timing_enable")
+
+    def read_timing(self) -> CKernelTimes:
+        """Average ms per step of the build and solve kernels (CUDA events on the launch
+        stream) since the last read."""
+        t = CKernelTimes()
+        self._check(self.L.osc_timing_read(self.h, C.byref(t)), "osc_timing_read")
+        return t
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.L.osc_kernel_launches(self.h))
+
+
+def measure_dfma_tflops(device: int = 0) -> float:
+    v = C.c_double()
+    rc = load().osc_measure_dfma_tflops(device, C.byref(v))
+    if rc:
+        raise OscError(f"osc_measure_dfma_tflops failed ({rc})")
+    return v.value

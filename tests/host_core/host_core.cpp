@@ -1,0 +1,77 @@
+// tests/host_core/host_core.cpp -- TEST HARNESS ONLY.
+// Instantiates the product's per-environment algorithm (csrc/osc_core.cuh) with
+// LANES = 1 on the host so that `pytest -m "not gpu"` can compare the exact code
+// the GPU runs against the oracle.  Never linked into libosc_b200.so.
+#include <cstring>
+#include <memory>
+
+#include "../../operational-space-control_b200/csrc/osc_params.h"
+
+namespace {
+template <class D>
+int run(const osc::Params& p, const double* M, const double* C, const double* J,
+        const double* bias, const double* targets, const double* mask, double* state, double* x,
+        double* y, double* torque, int* info_i, double* info_d, double* Hdv_out, double* f_out) {
+  using Core = osc::Core<D, 1>;
+  using B = osc::BuildQP<D>;
+  auto ws = std::make_unique<osc::Workspace<D>>();
+  std::memset(ws.get(), 0, sizeof(*ws));
+  // objective build (the build kernel's per-item functions)
+  double H[D::NV * D::NV], f[D::NV];
+  for (int a = 0; a < D::NV; ++a) {
+    for (int b = 0; b <= a; ++b) {
+      const double v = B::h_entry(J, p.w_row, p.w_reg, a, b);
+      H[a * D::NV + b] = v;
+      H[b * D::NV + a] = v;
+    }
+    f[a] = B::f_entry(J, bias, targets, p.w_row, a);
+  }
+  if (Hdv_out) std::memcpy(Hdv_out, H, sizeof(H));
+  if (f_out) std::memcpy(f_out, f, sizeof(f));
+  if (!state) return 0;
+  std::memcpy(ws->Ae, M, sizeof(double) * D::NV * D::NV);
+  std::memcpy(ws->Pdv, H, sizeof(H));
+  std::memcpy(ws->scratch, J + D::JC0 * D::NV, sizeof(double) * D::NZ * D::NV);
+  std::memcpy(ws->x, state, sizeof(double) * D::STATE);
+  std::memcpy(ws->Cv, C, sizeof(double) * D::NV);
+  std::memcpy(ws->fv, f, sizeof(f));
+  std::memcpy(ws->maskv, mask, sizeof(double) * D::NC);
+  osc::Result r = Core::step(*ws, p, 0, x, y, torque);
+  std::memcpy(state, ws->x, sizeof(double) * D::STATE);
+  info_i[0] = r.iter;
+  info_i[1] = r.status;
+  info_i[2] = r.rho_updates;
+  info_d[0] = r.pri_res;
+  info_d[1] = r.dua_res;
+  info_d[2] = r.rho;
+  return 0;
+}
+}  // namespace
+
+extern "C" int osc_core_host_state_size(const osc_robot_spec* spec) {
+  switch (osc::shape_of(*spec)) {
+    case osc::Shape::kWalter: return osc::WalterDims::STATE;
+    case osc::Shape::kGo2: return osc::Go2Dims::STATE;
+    default: return -1;
+  }
+}
+
+// state == NULL: only build H (nv*nv) and f (nv).  Otherwise run one control step:
+// state is the STATE-double record (all zeros + flag 0 => Init path), updated in place.
+extern "C" int osc_core_host_step(const osc_robot_spec* spec, const osc_settings* settings,
+                                  const double* M, const double* C, const double* J,
+                                  const double* bias, const double* targets, const double* mask,
+                                  double* state, double* x, double* y, double* torque,
+                                  int* info_i, double* info_d, double* Hdv_out, double* f_out) {
+  const osc::Params p = osc::make_params(*spec, *settings);
+  switch (osc::shape_of(*spec)) {
+    case osc::Shape::kWalter:
+      return run<osc::WalterDims>(p, M, C, J, bias, targets, mask, state, x, y, torque, info_i,
+                                  info_d, Hdv_out, f_out);
+    case osc::Shape::kGo2:
+      return run<osc::Go2Dims>(p, M, C, J, bias, targets, mask, state, x, y, torque, info_i,
+                               info_d, Hdv_out, f_out);
+    default:
+      return -1;
+  }
+}

@@ -1,0 +1,156 @@
+"""-m gpu: parity of the CUDA path (through the C-ABI) against the oracle.
+
+P1 (gate): torques within 1e-5 + 1e-4*|tau| of the oracle run with identical settings
+           (tolerance of BASELINE.json's north_star), same iteration count per environment.
+P2 (gate): OSQP's primal/dual residual test (eps_abs = eps_rel = 1e-3) passes on the GPU
+           exactly where it passes in the oracle (status equal).
+Integer gates: iteration counts and status codes are bit-exact; masked contacts give
+           exactly-zero contact forces' bounds (z in [0,0]) on both sides.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 1e-5, 1e-4  # north_star: "torques within 1e-4 relative and 1e-5 absolute"
+
+CASES = [
+    ("walter_sr", "standing", 512),
+    ("unitree_go2", "go2_standing", 1024),
+    ("walter_sr_true_tumbling_mjjoint", "tumbling", 1024),
+    ("walter_sr_wheels", "stairs", 1024),
+]
+
+
+def _compare(gpu, orc, tag):
+    keep = orc["margin"] > 1e-7  # thresholded decisions at round-off distance are excluded
+    assert keep.mean() > 0.999, tag
+    assert np.array_equal(gpu["iters"][keep], orc["iters"][keep]), tag
+    assert np.array_equal(gpu["status"][keep], orc["status"][keep]), tag
+    d = np.abs(gpu["torque"][keep] - orc["torque"][keep])
+    tol = ATOL + RTOL * np.abs(orc["torque"][keep])
+    assert (d <= tol).all(), f"{tag}: worst ratio {(d / tol).max()}"
+    np.testing.assert_allclose(gpu["rho"][keep], orc["rho"][keep], rtol=1e-4, err_msg=tag)
+    # P2: residuals reported by both sides agree and satisfy the same test
+    np.testing.assert_allclose(gpu["pri_res"][keep], orc["pri_res"][keep], rtol=1e-3, atol=1e-9)
+    np.testing.assert_allclose(gpu["dua_res"][keep], orc["dua_res"][keep], rtol=1e-3, atol=1e-9)
+    return float((d / tol).max())
+
+
+@pytest.mark.parametrize("preset,config,n_envs", CASES)
+def test_cold_and_warm_steps_match_oracle(oracle, preset, config, n_envs):
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    steps = [ob.synth.make_inputs(spec, n_envs, config, step=t) for t in range(3)]
+    ob_ = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    assert ob_.setup(steps[0]) == 0
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(steps[0])
+    for t, inp in enumerate(steps):
+        o = ob_.step(inp)
+        assert o["reinits"] == 0
+        tq = g.step(inp)
+        r = g.results()
+        assert np.array_equal(tq, r["torque"])
+        worst = _compare(r, o, f"{preset}/{config} step {t}")
+        print(f"{preset}/{config} step {t}: iters {np.bincount(o['iters'] // 25)} worst tol ratio {worst:.3g}")
+    # the reference's solution slice: torque = x[nv : nv+nu] (:631)
+    assert np.array_equal(r["torque"], r["x"][:, spec.nv:spec.nv + spec.nu])
+
+
+def test_fixed_budget_settings_match_oracle(oracle):
+    """P1 in its strict form: eps = 0 (never stops early), K iterations, rho update every R."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr_true_tumbling_mjjoint")
+    n_envs = 512
+    inp = ob.synth.make_inputs(spec, n_envs, "tumbling")
+    for K, R in ((100, 25), (200, 50)):
+        kw = dict(max_iter=K, eps_abs=0.0, eps_rel=0.0, adaptive_rho_interval=R)
+        o_ = oracle.OracleBatch(spec, n_envs, oracle.default_settings(**kw))
+        o_.setup(inp)
+        o = o_.step(inp)
+        g = capi.BatchedOSC(spec, n_envs, capi.default_settings(**kw))
+        g.setup(inp)
+        g.step(inp)
+        r = g.results()
+        assert (r["iters"] == K).all() and (o["iters"] == K).all()
+        keep = o["margin"] > 1e-7
+        d = np.abs(r["torque"] - o["torque"])[keep]
+        tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
+        assert (d <= tol).all(), (K, R, (d / tol).max())
+
+
+def test_contact_mask_edge_cases(oracle):
+    """all contacts off => z == 0 (bounds [0,0]); all on; a single contact."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr")
+    n_envs = 256
+    inp = ob.synth.make_inputs(spec, n_envs, "tumbling")
+    inp["mask"][:64] = 0.0
+    inp["mask"][64:128] = 1.0
+    inp["mask"][128:192] = 0.0
+    inp["mask"][128:192, 3] = 1.0
+    o_ = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    o_.setup(inp)
+    o = o_.step(inp)
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(inp)
+    g.step(inp)
+    r = g.results()
+    _compare(r, o, "mask edge cases")
+    z = r["x"][:, spec.nv + spec.nu:]
+    zc = z.reshape(n_envs, spec.nc, 3)
+    off = inp["mask"] == 0.0
+    # contact c <-> z[3c:3c+3] <-> mask[c]: forces of masked-out contacts are ~0 (equality rows)
+    assert np.abs(zc[off]).max() < 1e-2
+    assert np.abs(zc[128:192, 3]).max() > 1e-3
+
+
+def test_reset_warm_start_and_state_order(oracle):
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("unitree_go2")
+    n_envs = 256
+    inp = ob.synth.make_inputs(spec, n_envs, "go2_standing")
+    g = capi.BatchedOSC(spec, n_envs)
+    with pytest.raises(capi.OscError):
+        g.step(inp)  # control_loop before set_up_optimization
+    g.setup(inp)
+    a = g.step(inp)
+    it_cold = g.results()["iters"].copy()
+    b = g.step(inp)
+    it_warm = g.results()["iters"].copy()
+    assert it_warm.mean() < it_cold.mean()
+    np.testing.assert_allclose(a, b, atol=5e-1)  # both inside OSQP's loose default tolerance
+
+
+def test_full_size_properties():
+    """BASELINE sizes (16384 Walter envs): size-independent checks -- every environment
+    solved, OSQP's residual test holds, dynamics equality satisfied to the primal
+    tolerance, torque and friction-pyramid bounds respected within it."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr_true_tumbling_mjjoint")
+    n_envs = 16384
+    inp = ob.synth.make_inputs(spec, n_envs, "tumbling")
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(inp)
+    g.step(inp)
+    r = g.results()
+    assert (r["status"] == capi.SOLVED).all()
+    assert (r["iters"] % 25 == 0).all()
+    x = r["x"]
+    dv, u, z = x[:, :spec.nv], x[:, spec.nv:spec.nv + spec.nu], x[:, spec.nv + spec.nu:]
+    Jc = inp["J"][:, 3 * spec.ns - spec.nz:3 * spec.ns, :]  # (N, nz, nv) = Jc'
+    dyn = (np.einsum("bij,bj->bi", inp["M"], dv) + inp["C"]
+           - np.concatenate([np.zeros((n_envs, spec.nv - spec.nu)), u], 1)
+           - np.einsum("bki,bk->bi", Jc, z))
+    scale = 1.0 + np.abs(inp["C"]).max(1)
+    assert (np.abs(dyn).max(1) <= 2e-3 * scale + r["pri_res"] * 1.0001 + 1e-9).all()
+    assert (u <= np.array(spec.u_ub) + r["pri_res"][:, None] + 1e-9).all()
+    zc = z.reshape(n_envs, spec.nc, 3)
+    cone = np.abs(zc[..., 0]) + np.abs(zc[..., 1]) - spec.mu * zc[..., 2]
+    assert (cone <= r["pri_res"][:, None] * 4 + 1e-6).all()
