@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""bench.py -- OSC solves/sec of the batched operational-space controller.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+A "step" is one control step of every environment: the hot path
+(update_optimization_data -> update_optimization -> solve_optimization -> torque slice,
+reference walter_sr/operational_space_controller.h:515-631) over one batch of synthetic
+OSCData, warm-started from the previous step like the reference's control_loop.  Step t
+uses the t-th "control tick" of the synthetic environments (1 % drift per tick), cycling
+through NSETS resident batches.
+
+value      whole-job solves/s with inputs resident in HBM (device-timed, max over ranks)
+e2e        same metric through the C-ABI with pinned HOST buffers: H2D of the step's
+           inputs + step + D2H of the torques inside the timed region
+roofline   dominant kernel (solve_kernel): algorithmic FLOPs / CUDA-event time vs the
+           measured FP64-FMA peak; `roofline_build` is the HBM-bound build kernel
+cpu_baseline  the oracle (restatement of the reference's CPU path, "port") on the box's
+           host cores, bounded sample, same protocol
+--impl reference   times that CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "operational-space-control_b200", "python"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]/[4]: Walter Sr tumbling with body targets, 16384 envs per GPU
+    "walter_sr_tumbling_16384_per_gpu": dict(preset="walter_sr_true_tumbling_mjjoint",
+                                             config="tumbling", envs=16384),
+    # configs[1]
+    "go2_standing_4096": dict(preset="unitree_go2", config="go2_standing", envs=4096),
+    # configs[3]
+    "walter_sr_wheels_stairs_8192_per_gpu": dict(preset="walter_sr_wheels", config="stairs",
+                                                 envs=8192),
+    # configs[0] (the reference's own single-robot case, batched)
+    "walter_sr_standing_4096": dict(preset="walter_sr", config="standing", envs=4096),
+}
+DEFAULT_WORKLOAD = "walter_sr_tumbling_16384_per_gpu"
+NSETS = 4
+FIELDS = ("M", "C", "J", "bias", "targets", "mask")
+METRIC = "OSC solves/sec (whole box)"
+UNIT = "solves/s"
+
+
+def algorithmic_flops_per_solve(spec, k_mean):
+    """dense-reduced-form operation count of the solver part (the H/f build
+    is the other kernel): reduced system + Cholesky once, per-iteration solve + products,
+    per-check residuals every 25 iterations."""
+    n, nv, nc = spec.n, spec.nv, spec.nc
+    setup = nv * n * n + n ** 3 / 3.0
+    nnzA = nv * n + 12 * nc + n
+    per_iter = 2 * 2 * nnzA + 2 * n * n + 12 * spec.m
+    per_check = 2 * n * n + 2 * nnzA
+    return setup + per_iter * k_mean + per_check * np.ceil(k_mean / 25.0)
+
+
+def build_bytes_per_solve(spec):
+    """build kernel: reads J, bias, targets; writes H (dv block) and f."""
+    return 8 * (spec.s * spec.nv + 2 * spec.s + spec.nv * spec.nv + spec.nv)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv",
+                                       "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        lines = [l.strip() for l in self.f.read().splitlines()[1:] if l.strip()]
+        sm, mx, reasons = [], [], set()
+        for l in lines:
+            c = [x.strip() for x in l.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1].split()[0]))
+                mx.append(float(c[2].split()[0]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]  # samples under load are the upper half
+            out.update(sm_mhz=float(np.median(top)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except Exception:
+            pass
+        return out
+
+
+def cpu_leg(spec, wl, sample_envs, steps, warmup, n_threads=0):
+    """The reference's CPU path (oracle port), all host threads, same warm-step protocol on
+    a bounded sample of the workload.  Returns (solves/s, info dict)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import osc_oracle as orc
+    import osc_b200 as ob
+    try:
+        orc.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    s = orc.default_settings(linsys=1)  # reduced Cholesky: the faster of the two equivalent forms
+    b = orc.OracleBatch(spec, sample_envs, s, native=native)
+    threads = n_threads or b.max_threads
+    sets = [ob.synth.make_inputs(spec, sample_envs, wl["config"], step=t) for t in range(NSETS)]
+    b.setup(sets[0], threads)
+    iters = []
+    for t in range(warmup):
+        o = b.step(sets[t % NSETS], threads)
+    t0 = time.perf_counter()
+    for t in range(warmup, warmup + steps):
+        o = b.step(sets[t % NSETS], threads)
+        iters.append(float(o["iters"].mean()))
+    dt = time.perf_counter() - t0
+    value = sample_envs * steps / dt
+    info = dict(value=value, unit=UNIT, cores=threads, kind="port",
+                sample=f"{sample_envs} envs x {steps} warm control steps of the same workload "
+                       f"(oracle: restatement of the reference's QP build + OSQP 0.6.3, "
+                       f"{'-march=native' if native else 'x86-64-v3'}, reduced-Cholesky KKT); "
+                       f"{dt:.2f} s wall",
+                iters_mean=float(np.mean(iters)), us_per_solve_per_core=1e6 * threads / value)
+    return value, info
+
+
+def run_reference(args, wl, spec):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(wl["envs"], 2048)
+    value, info = cpu_leg(spec, wl, sample, args.steps, args.warmup)
+    ms = 1e3 * sample / value
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "envs_per_step": sample,
+                       "warm_start": True, "note": "CPU path on host cores; each step is a "
+                       "bounded sample of the workload"},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    import osc_b200 as ob
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs_per_gpu:
+        wl["envs"] = args.envs_per_gpu
+    spec = ob.load_preset(wl["preset"])
+    if args.impl == "reference":
+        return run_reference(args, wl, spec)
+
+    import torch
+    import torch.distributed as dist
+    from osc_b200 import capi, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n_envs = wl["envs"]
+    first_env = rank * n_envs  # weak scaling: fixed envs per GPU, disjoint environments
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- synthetic control ticks: NSETS batches in pinned host memory and in HBM
+    host_sets, dev_sets = [], []
+    for t in range(NSETS):
+        inp = ob.synth.make_inputs(spec, n_envs, wl["config"], first_env=first_env, step=t)
+        pinned = {}
+        for k in FIELDS:
+            a = capi.pinned_empty(inp[k].shape)
+            a[...] = inp[k]
+            pinned[k] = a
+        host_sets.append(pinned)
+        dev_sets.append({k: torch.from_numpy(inp[k]).to(dev) for k in FIELDS})
+    in_bytes = sum(host_sets[0][k].nbytes for k in FIELDS)
+    out_bytes = n_envs * spec.nu * 8
+
+    osc = capi.BatchedOSC(spec, n_envs, device=local)
+
+    def bind(t):
+        d = dev_sets[t % NSETS]
+        osc.bind_device_inputs(*[d[k].data_ptr() for k in FIELDS])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value)
+    bind(0)
+    osc.setup(stream=stream)
+    for t in range(args.warmup):
+        bind(t)
+        osc.step_device(stream)
+    osc.enable_timing(True)
+    launches0 = osc.kernel_launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i, t in enumerate(range(args.warmup, args.warmup + args.steps)):
+        bind(t)
+        osc.step_device(stream)
+        evs[i + 1].record()
+    barrier()
+    ms_total = sharding.max_over_ranks(evs[0].elapsed_time(evs[-1]), dev)
+    p50_ms = sharding.max_over_ranks(
+        float(np.median([a.elapsed_time(b) for a, b in zip(evs, evs[1:])])), dev)
+    clocks = sampler.stop() if sampler else None
+    launches = osc.kernel_launches - launches0
+    kt = osc.read_timing()
+    osc.enable_timing(False)
+    res = osc.results(stream)
+    ms_per_step = ms_total / args.steps
+    value = world * n_envs / (ms_per_step * 1e-3)
+    k_mean = float(res["iters"].mean())
+    stats = sharding.reduce_stats(dict(solved=int((res["status"] == capi.SOLVED).sum()),
+                                       iters=float(res["iters"].sum()),
+                                       launches=int(launches)), world, dev)
+
+    # ---- cold first step (reported beside the steady state)
+    bind(0)
+    osc.setup(stream=stream)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    osc.step_device(stream)
+    c1.record()
+    barrier()
+    cold_ms = sharding.max_over_ranks(c0.elapsed_time(c1), dev)
+    cold_iters = float(osc.results(stream)["iters"].mean())
+
+    # ---- end to end through the C-ABI with host buffers (e2e)
+    osc.bind_device_inputs()  # back to the handle's own input buffers
+    tq = capi.pinned_empty((n_envs, spec.nu))
+    ptrs = [[host_sets[t][k].ctypes.data for k in FIELDS] for t in range(NSETS)]
+    osc.setup(host_sets[0], stream)
+    for t in range(args.warmup):
+        osc.step_host_into(ptrs[t % NSETS], tq, stream)
+    barrier()
+    w0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for t in range(args.warmup, args.warmup + args.steps):
+        osc.step_host_into(ptrs[t % NSETS], tq, stream)
+    g1.record()
+    barrier()
+    e2e_ms = sharding.max_over_ranks(g0.elapsed_time(g1), dev) / args.steps
+    e2e_wall_ms = sharding.max_over_ranks(1e3 * (time.perf_counter() - w0), dev) / args.steps
+    e2e_value = world * n_envs / (e2e_ms * 1e-3)
+
+    # ---- off the hot path: one all-gather of torques + statistics
+    gather_ms = None
+    if world > 1:
+        tq_dev = torch.from_numpy(np.ascontiguousarray(tq)).to(dev)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        allt = sharding.all_gather_rows(tq_dev, world * n_envs, world)
+        a1.record()
+        barrier()
+        assert allt.shape[0] == world * n_envs
+        gather_ms = sharding.max_over_ranks(a0.elapsed_time(a1), dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    dfma_peak = capi.measure_dfma_tflops(local)
+    flops = algorithmic_flops_per_solve(spec, k_mean) * n_envs
+    solve_tflops = flops / (kt.solve_ms * 1e-3) / 1e12
+    build_gbs = build_bytes_per_solve(spec) * n_envs / (kt.build_ms * 1e-3) / 1e9
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    tr = traffic.get(args.workload, {})
+    roofline = {"kernel": "solve_kernel", "bound": "fp64_fma", "achieved": solve_tflops,
+                "peak": dfma_peak, "unit": "TFLOP/s", "frac": solve_tflops / dfma_peak,
+                "traffic": tr.get("solve_kernel_dram_bytes_per_launch"),
+                "peak_source": "DFMA micro-benchmark run inside this bench "
+                               "(MEASURED_PEAKS.json has no FP64 entry)",
+                "algorithmic_flops_per_solve": flops / n_envs, "iters_mean": k_mean,
+                "launch_ms": kt.solve_ms,
+                "hbm_view": {"achieved_gbs": spec.algorithmic_bytes * n_envs / (kt.solve_ms * 1e-3) / 1e9,
+                             "peak_gbs": hbm_peak}}
+    roofline_build = {"kernel": "build_qp_kernel", "bound": "hbm", "achieved": build_gbs,
+                      "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
+                      "traffic": tr.get("build_qp_kernel_dram_bytes_per_launch"),
+                      "peak_source": hbm_src, "launch_ms": kt.build_ms,
+                      "algorithmic_bytes_per_solve": build_bytes_per_solve(spec)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "robot": spec.robot, "preset": wl["preset"],
+                       "envs_per_gpu": n_envs, "total_envs": world * n_envs,
+                       "warm_start": True, "osqp_settings": "OsqpSettings() defaults",
+                       "inputs_exceed_l2": bool(in_bytes > 126e6),
+                       "resident_input_sets": NSETS, "parallelism": f"env-sharded x{world}"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms,
+                    "wall_ms_per_step": e2e_wall_ms},
+            "gpu_launches": int(stats["launches"]),
+            "roofline": roofline, "roofline_build": roofline_build,
+            "p50_batch_latency_ms": p50_ms,
+            "solved_frac": stats["solved"] / (world * n_envs),
+            "cold_start": {"ms_per_step": cold_ms, "value": world * n_envs / (cold_ms * 1e-3),
+                           "iters_mean": cold_iters},
+            "torque_all_gather_ms": gather_ms}
+    if world == 1 and not args.no_cpu_baseline:
+        sample = min(n_envs, 2048)
+        _, info = cpu_leg(spec, wl, sample, steps=6, warmup=2)
+        line["cpu_baseline"] = info
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

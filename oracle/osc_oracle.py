@@ -185,3 +185,54 @@ class OracleBatch:
         D = np.zeros(sp.n); E = np.zeros(sp.m); c = np.zeros(1)
         self.L.orc_batch_scaled_state(self.h, e, _p(x), _p(z), _p(y), _p(D), _p(E), _p(c))
         return dict(x=x, z=z, y=y, D=D, E=E, c=float(c[0]))
+
+
+# ---------------------------------------------------------------------------
+# generic QP interface of the OSQP restatement (used to pin it on known answers)
+# ---------------------------------------------------------------------------
+class _Csc(C.Structure):
+    _fields_ = [("n_rows", C.c_int), ("n_cols", C.c_int), ("nnz", C.c_int),
+                ("p", C.POINTER(C.c_int)), ("i", C.POINTER(C.c_int)), ("x", C.POINTER(C.c_double))]
+
+
+def solve_qp(P, q, A, l, u, settings: Settings | None = None, warm=None, n_solves: int = 1):
+    """min 1/2 x'Px + q'x  s.t. l <= Ax <= u  through orc_setup/orc_solve."""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_csc_from_dense.restype = C.POINTER(_Csc)
+    L.orc_csc_from_dense.argtypes = [dp, C.c_int, C.c_int, C.c_int]
+    L.orc_csc_free.argtypes = [C.POINTER(_Csc)]
+    L.orc_setup.restype = C.c_void_p
+    L.orc_setup.argtypes = [C.POINTER(_Csc), dp, C.POINTER(_Csc), dp, dp, C.POINTER(Settings)]
+    L.orc_solve.argtypes = [C.c_void_p]
+    L.orc_cleanup.argtypes = [C.c_void_p]
+    L.orc_warm_start.argtypes = [C.c_void_p, dp, dp]
+    L.orc_get_info.restype = C.POINTER(Info)
+    L.orc_get_info.argtypes = [C.c_void_p]
+    L.orc_solution_x.restype = dp
+    L.orc_solution_x.argtypes = [C.c_void_p]
+    L.orc_solution_y.restype = dp
+    L.orc_solution_y.argtypes = [C.c_void_p]
+    L.orc_get_rho.restype = C.c_double
+    L.orc_get_rho.argtypes = [C.c_void_p]
+    P = np.asarray(P, float); A = np.asarray(A, float)
+    q = _c(q); l = _c(l); u = _c(u)
+    n, m = P.shape[0], A.shape[0]
+    s = settings if settings is not None else default_settings()
+    Pc = L.orc_csc_from_dense(_p(np.ascontiguousarray(P.T).ravel()), n, n, 1)
+    Ac = L.orc_csc_from_dense(_p(np.ascontiguousarray(A.T).ravel()), m, n, 0)
+    w = L.orc_setup(Pc, _p(q), Ac, _p(l), _p(u), C.byref(s))
+    L.orc_csc_free(Pc); L.orc_csc_free(Ac)
+    if not w:
+        raise RuntimeError("orc_setup failed")
+    if warm is not None:
+        L.orc_warm_start(w, _p(_c(warm[0])), _p(_c(warm[1])))
+    for _ in range(n_solves):
+        L.orc_solve(w)
+    info = L.orc_get_info(w).contents
+    out = dict(x=np.array([L.orc_solution_x(w)[i] for i in range(n)]),
+               y=np.array([L.orc_solution_y(w)[i] for i in range(m)]),
+               iter=info.iter, status=info.status, pri_res=info.pri_res, dua_res=info.dua_res,
+               rho=L.orc_get_rho(w), rho_updates=info.rho_updates)
+    L.orc_cleanup(w)
+    return out

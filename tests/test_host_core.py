@@ -1,0 +1,97 @@
+"""CPU: the product's per-environment algorithm (csrc/osc_core.cuh), instantiated with a
+single lane on the host by tests/host_core, against the oracle.  This checks the *device
+code's* arithmetic (structured KKT elimination, scaling, rho rules, termination) without a
+GPU; the GPU tests check the same code as the kernels actually run it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+FIELDS = ("M", "C", "J", "bias", "targets", "mask")
+ATOL, RTOL = 1e-5, 1e-4
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def run_host_core(L, spec, settings, steps, n_envs):
+    from osc_b200 import capi
+    cs = capi.c_spec(spec)
+    SS = L.osc_core_host_state_size(C.byref(cs))
+    assert SS == spec.n + 2 * spec.m + spec.nv + 2
+    outs = [dict(torque=np.zeros((n_envs, spec.nu)), iters=np.zeros(n_envs, np.int32),
+                 status=np.zeros(n_envs, np.int32), rho=np.zeros(n_envs),
+                 x=np.zeros((n_envs, spec.n)), y=np.zeros((n_envs, spec.m))) for _ in steps]
+    ii = np.zeros(3, np.int32)
+    dd = np.zeros(3)
+    for e in range(n_envs):
+        state = np.zeros(SS)
+        H = np.zeros(spec.nv ** 2)
+        f = np.zeros(spec.nv)
+        a = [np.ascontiguousarray(steps[0][k][e]) for k in FIELDS]
+        L.osc_core_host_step(C.byref(cs), C.byref(settings), *[_p(v) for v in a], None, None,
+                             None, None, None, None, _p(H), _p(f))
+        # osc_setup's state: cold iterates, previous linear cost = f, rho0, initialised
+        q0 = spec.n + 2 * spec.m
+        state[q0:q0 + spec.nv] = f
+        state[-2], state[-1] = settings.rho, 1.0
+        for t, data in enumerate(steps):
+            a = [np.ascontiguousarray(data[k][e]) for k in FIELDS]
+            x = np.zeros(spec.n); y = np.zeros(spec.m); tq = np.zeros(spec.nu)
+            L.osc_core_host_step(C.byref(cs), C.byref(settings), *[_p(v) for v in a], _p(state),
+                                 _p(x), _p(y), _p(tq), ii.ctypes.data_as(C.POINTER(C.c_int)),
+                                 _p(dd), None, None)
+            o = outs[t]
+            o["torque"][e], o["x"][e], o["y"][e] = tq, x, y
+            o["iters"][e], o["status"][e], o["rho"][e] = ii[0], ii[1], dd[2]
+    return outs
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_true_tumbling_mjjoint", "tumbling"),
+                                           ("unitree_go2", "go2_standing"),
+                                           ("walter_sr_wheels", "stairs")])
+def test_device_algorithm_matches_oracle_on_host(oracle, host_core, preset, config):
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    N = 48
+    steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(2)]
+    b = oracle.OracleBatch(spec, N, oracle.default_settings())
+    b.setup(steps[0])
+    ref = [b.step(s) for s in steps]
+    st = capi.CSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 5.0, 10, 1, 0, 4000, 25, 1)
+    got = run_host_core(host_core, spec, st, steps, N)
+    for t in range(2):
+        o, g = ref[t], got[t]
+        keep = o["margin"] > 1e-7
+        np.testing.assert_array_equal(g["iters"][keep], o["iters"][keep])
+        np.testing.assert_array_equal(g["status"][keep], o["status"][keep])
+        d = np.abs(g["torque"] - o["torque"])[keep]
+        tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
+        assert (d <= tol).all(), (preset, t, (d / tol).max())
+    assert ref[1]["iters"].mean() < ref[0]["iters"].mean()  # warm start carried over
+
+
+def test_objective_build_is_bitwise_close_to_oracle(oracle, host_core):
+    """H (dv block) and f of the build kernel's per-entry functions vs orc_build_qp."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    for preset, config in (("walter_sr", "tumbling"), ("unitree_go2", "go2_standing")):
+        spec = ob.load_preset(preset)
+        inp = ob.synth.make_inputs(spec, 3, config)
+        cs = capi.c_spec(spec)
+        st = capi.CSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 5.0, 10, 1, 0, 4000, 25, 1)
+        for e in range(3):
+            a = [np.ascontiguousarray(inp[k][e]) for k in FIELDS]
+            H = np.zeros(spec.nv ** 2)
+            f = np.zeros(spec.nv)
+            host_core.osc_core_host_step(C.byref(cs), C.byref(st), *[_p(v) for v in a], None,
+                                         None, None, None, None, None, _p(H), _p(f))
+            Ho, fo, *_ = oracle.build_qp(spec, *a)
+            np.testing.assert_allclose(H.reshape(spec.nv, spec.nv), Ho[:spec.nv, :spec.nv],
+                                       rtol=1e-13, atol=1e-10)
+            np.testing.assert_allclose(f, fo[:spec.nv], rtol=1e-13, atol=1e-9)
+            assert np.all(fo[spec.nv:] == 0.0)
+            np.testing.assert_array_equal(np.diag(Ho)[spec.nv:spec.nv + spec.nu],
+                                          2 * (spec.w_reg + spec.w_torque))
