@@ -78,7 +78,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv",
-                                       "-lms", "100", "-i", str(gpu_index)],
+                                       "-lms", "20", "-i", str(gpu_index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -179,7 +179,7 @@ def run_reference(args, wl, spec):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
@@ -248,6 +248,8 @@ def main():
     osc.enable_timing(True)
     launches0 = osc.kernel_launches
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)  # let nvidia-smi start sampling before the timed region
     barrier()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record()
@@ -374,7 +376,7 @@ def main():
             "torque_all_gather_ms": gather_ms}
     if world == 1 and not args.no_cpu_baseline:
         sample = min(n_envs, 2048)
-        _, info = cpu_leg(spec, wl, sample, steps=6, warmup=2)
+        _, info = cpu_leg(spec, wl, sample, steps=40, warmup=2)
         line["cpu_baseline"] = info
     print(json.dumps(line))
     if world > 1:
