@@ -21,6 +21,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -73,7 +74,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ---------------------------------------------------------------------------
-// K2: objective build
+// K2: objective build.  One warp per environment; every warp owns a 2-stage ring of TMA
+// bulk copies (J, bias, targets of one environment per stage).  H = 2 J'WJ + 2 w_reg I is
+// produced in 2x2 register tiles of its lower triangle (one tile per lane, two 16-byte
+// shared-memory loads feed four FMAs per weighted row), f = 2 J'W(bias - t) by the
+// remaining lanes, four entries each.  Rows with zero weight are skipped (warp-uniform).
 // ---------------------------------------------------------------------------
 template <class D>
 struct BuildStage {
@@ -81,76 +86,120 @@ struct BuildStage {
   double bias[D::S];
   double targets[D::S];
 };
-constexpr int kBuildStages = 3;
+constexpr int kBuildStages = 2;
+constexpr int kBuildWarps = 4;
 
 template <class D>
-constexpr int build_threads() {
-  return ((BuildQP<D>::NITEM + 31) / 32) * 32;
-}
-
-template <class D>
-__global__ void __launch_bounds__(build_threads<D>())
+__global__ void __launch_bounds__(kBuildWarps * 32)
 build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
                 const double* __restrict__ bias, const double* __restrict__ targets,
                 double* __restrict__ Hdv, double* __restrict__ fdv, int n_envs) {
-  using B = BuildQP<D>;
-  constexpr int NV = D::NV, S = D::S;
+  constexpr int NV = D::NV, S = D::S, NS = D::NS;
+  constexpr int NT = NV / 2;                 // tiles per side
+  constexpr int NTILE = NT * (NT + 1) / 2;   // lower-triangle 2x2 tiles
+  constexpr int NFG = (NV + 3) / 4;          // groups of 4 entries of f
+  constexpr int NITEM = NTILE + NFG;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BuildStage<D>* stages = reinterpret_cast<BuildStage<D>*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kBuildStages * sizeof(BuildStage<D>));
-  double* w_row = reinterpret_cast<double*>(bars + kBuildStages);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kBuildWarps * kBuildStages * sizeof(BuildStage<D>));
+  double* w_row = reinterpret_cast<double*>(bars + kBuildWarps * kBuildStages);
 
-  const int tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  BuildStage<D>* my = stages + warp * kBuildStages;
+  uint64_t* mybar = bars + warp * kBuildStages;
   constexpr uint32_t kBytes = sizeof(BuildStage<D>);
   auto issue = [&](int stage, int env) {
-    BuildStage<D>& st = stages[stage];
-    mbar_expect_tx(&bars[stage], kBytes);
-    bulk_g2s(st.J, J + (size_t)env * S * NV, sizeof(st.J), &bars[stage]);
-    bulk_g2s(st.bias, bias + (size_t)env * S, sizeof(st.bias), &bars[stage]);
-    bulk_g2s(st.targets, targets + (size_t)env * S, sizeof(st.targets), &bars[stage]);
+    BuildStage<D>& st = my[stage];
+    mbar_expect_tx(&mybar[stage], kBytes);
+    bulk_g2s(st.J, J + (size_t)env * S * NV, sizeof(st.J), &mybar[stage]);
+    bulk_g2s(st.bias, bias + (size_t)env * S, sizeof(st.bias), &mybar[stage]);
+    bulk_g2s(st.targets, targets + (size_t)env * S, sizeof(st.targets), &mybar[stage]);
   };
-  if (tid == 0) {
-    for (int s = 0; s < kBuildStages; ++s) mbar_init(&bars[s], 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBuildWarps * kBuildStages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
-  for (int k = tid; k < S; k += blockDim.x) w_row[k] = p.w_row[k];
+  for (int k = threadIdx.x; k < S; k += blockDim.x) w_row[k] = p.w_row[k];
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < kBuildStages; ++s) {
-      const int env = blockIdx.x + s * gridDim.x;
-      if (env < n_envs) issue(s, env);
-    }
+  const int stride = gridDim.x * kBuildWarps;
+  const int env0 = blockIdx.x * kBuildWarps + warp;
+  if (lane == 0) {
+    for (int s = 0; s < kBuildStages; ++s)
+      if (env0 + s * stride < n_envs) issue(s, env0 + s * stride);
   }
-  // this thread's output entry
-  int a = 0, b = 0;
-  const bool is_h = tid < B::NPAIR, is_f = !is_h && tid < B::NITEM;
-  if (is_h) {
-    int t = tid;
-    while (t > a) {  // lower triangle, row by row
-      t -= a + 1;
-      ++a;
-    }
-    b = t;
-  } else if (is_f) {
-    a = tid - B::NPAIR;
-  }
+  const double two_wreg = 2.0 * p.w_reg;
   int it = 0;
-  for (int env = blockIdx.x; env < n_envs; env += gridDim.x, ++it) {
+  for (int env = env0; env < n_envs; env += stride, ++it) {
     const int stage = it % kBuildStages;
-    const uint32_t parity = (it / kBuildStages) & 1;
-    mbar_wait(&bars[stage], parity);
-    const BuildStage<D>& st = stages[stage];
-    if (is_h) {
-      const double v = B::h_entry(st.J, w_row, p.w_reg, a, b);
-      double* H = Hdv + (size_t)env * NV * NV;
-      H[a * NV + b] = v;
-      H[b * NV + a] = v;
-    } else if (is_f) {
-      fdv[(size_t)env * NV + a] = B::f_entry(st.J, st.bias, st.targets, w_row, a);
+    mbar_wait(&mybar[stage], (it / kBuildStages) & 1);
+    const BuildStage<D>& st = my[stage];
+    for (int item = lane; item < NITEM; item += 32) {
+      if (item < NTILE) {
+        int ta = 0, t = item;
+        while (t > ta) {
+          t -= ta + 1;
+          ++ta;
+        }
+        const int a = 2 * ta, b = 2 * t;  // tile rows a,a+1 ; cols b,b+1 ; b <= a
+        double h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+#pragma unroll 2
+        for (int k = 0; k < S; ++k) {
+          const double wk = w_row[k];
+          if (wk != 0.0) {
+            const double2 ja = *reinterpret_cast<const double2*>(&st.J[k * NV + a]);
+            const double2 jb = *reinterpret_cast<const double2*>(&st.J[k * NV + b]);
+            const double wa0 = wk * ja.x, wa1 = wk * ja.y;
+            h00 += wa0 * jb.x;
+            h01 += wa0 * jb.y;
+            h10 += wa1 * jb.x;
+            h11 += wa1 * jb.y;
+          }
+        }
+        h00 *= 2.0; h01 *= 2.0; h10 *= 2.0; h11 *= 2.0;
+        double* H = Hdv + (size_t)env * NV * NV;
+        if (a == b) {
+          // diagonal tile: h01 and h10 were accumulated as (w Ja)Jb with the operand order
+          // of the lower-triangle entry (a+1, a); mirror that one like the reference's H
+          h00 += two_wreg;
+          h11 += two_wreg;
+          *reinterpret_cast<double2*>(&H[a * NV + a]) = make_double2(h00, h10);
+          *reinterpret_cast<double2*>(&H[(a + 1) * NV + a]) = make_double2(h10, h11);
+        } else {
+          *reinterpret_cast<double2*>(&H[a * NV + b]) = make_double2(h00, h01);
+          *reinterpret_cast<double2*>(&H[(a + 1) * NV + b]) = make_double2(h10, h11);
+          *reinterpret_cast<double2*>(&H[b * NV + a]) = make_double2(h00, h10);
+          *reinterpret_cast<double2*>(&H[(b + 1) * NV + a]) = make_double2(h01, h11);
+        }
+      } else {
+        const int a = 4 * (item - NTILE);
+        double g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        for (int k = 0; k < S; ++k) {
+          const double wk = w_row[k];
+          if (wk != 0.0) {
+            const int kr = (k < 3 * NS) ? k : k - 3 * NS;
+            const int site = kr / 3, kk = kr - 3 * site;
+            const double r = st.bias[k] - st.targets[site * 6 + ((k < 3 * NS) ? kk : 3 + kk)];
+            const double* jr = &st.J[k * NV + a];
+            g0 += (wk * jr[0]) * r;
+            g1 += (wk * jr[1]) * r;
+            if (a + 2 < NV) {
+              g2 += (wk * jr[2]) * r;
+              g3 += (wk * jr[3]) * r;
+            }
+          }
+        }
+        double* f = fdv + (size_t)env * NV + a;
+        f[0] = 2.0 * g0;
+        f[1] = 2.0 * g1;
+        if (a + 2 < NV) {
+          f[2] = 2.0 * g2;
+          f[3] = 2.0 * g3;
+        }
+      }
     }
-    __syncthreads();  // everyone is done with this stage
-    if (tid == 0) {
-      const int next = env + kBuildStages * gridDim.x;
+    __syncwarp();  // the whole warp is done reading this stage
+    if (lane == 0) {
+      const int next = env + kBuildStages * stride;
       if (next < n_envs) issue(stage, next);
     }
   }
@@ -230,18 +279,16 @@ solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
       bulk_g2s(w.Pdv, a.Hdv + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
       bulk_g2s(w.scratch, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(double) * D::NZ * NV,
                bar);
-      bulk_g2s(w.x, a.state + (size_t)env * D::STATE, sizeof(double) * D::STATE, bar);
+      bulk_g2s(w.land, a.state + (size_t)env * D::STATE, sizeof(double) * D::STATE, bar);
       bulk_g2s(w.Cv, a.C + (size_t)env * NV, sizeof(double) * NV, bar);
       bulk_g2s(w.fv, a.fdv + (size_t)env * NV, sizeof(double) * NV, bar);
       bulk_g2s(w.maskv, a.mask + (size_t)env * D::NC, sizeof(double) * D::NC, bar);
     }
     mbar_wait(bar, parity);
     parity ^= 1;
-    const Result r = C32::step(w, p, lane, a.sol_x + (size_t)env * D::N,
-                               a.sol_y + (size_t)env * D::M, a.torque + (size_t)env * D::NU);
-    double* st = a.state + (size_t)env * D::STATE;
-    const double* ws = w.x;  // x z y qprev rho_flag are contiguous
-    for (int i = lane; i < D::STATE; i += 32) st[i] = ws[i];
+    const Result r = C32::step(w, p, lane, a.fdv + (size_t)env * NV, a.sol_x + (size_t)env * D::N,
+                               a.sol_y + (size_t)env * D::M, a.torque + (size_t)env * D::NU,
+                               a.state + (size_t)env * D::STATE);
     if (lane == 0) {
       a.iters[env] = r.iter;
       a.status[env] = r.status;
@@ -288,6 +335,12 @@ struct osc_handle {
   int *dIters, *dStatus, *dCounter;
   // inputs actually read by the kernels (own buffers unless osc_bind_device_inputs)
   const double *iM, *iC, *iJ, *iBias, *iTargets, *iMask;
+  // pipelined host path: copy stream + per-chunk events and work counters
+  cudaStream_t copy_stream;
+  std::vector<cudaEvent_t> chunk_ev;
+  cudaEvent_t fence_ev;
+  int n_counters;
+  int solve_warps_pref;
   // optional per-kernel timing
   bool timing;
   std::vector<cudaEvent_t> ev;  // 3 events per recorded step
@@ -309,27 +362,37 @@ thread_local std::string g_create_err;
   } while (0)
 
 template <class D>
-constexpr int solve_warps() {
-  // as many warps (environments) per CTA as fit in 227 KB of shared memory, capped
-  return (int)((227 * 1024 - 256) / sizeof(osc::Workspace<D>)) > 16
+constexpr int max_solve_warps() {
+  // as many warps (environments) per CTA as fit in 227 KB of shared memory, at most 16
+  return (int)((227 * 1024 - 128) / sizeof(osc::Workspace<D>)) > 16
              ? 16
-             : (int)((227 * 1024 - 256) / sizeof(osc::Workspace<D>));
+             : (int)((227 * 1024 - 128) / sizeof(osc::Workspace<D>));
 }
+// Registers are allocated per SM sub-partition: 13-16 warps per CTA leave 128 registers per
+// thread, 9-12 warps leave 168.  Both variants are built; OSC_B200_SOLVE_WARPS=12|16 picks
+// one (default 12: no spills, same throughput).
+template <class D>
+constexpr int solve_warps_hi() { return max_solve_warps<D>(); }
+template <class D>
+constexpr int solve_warps_lo() { return max_solve_warps<D>() > 12 ? 12 : max_solve_warps<D>(); }
 
 template <class D>
-int launch_build(osc_handle* h, cudaStream_t st) {
-  constexpr int threads = osc::build_threads<D>();
-  const size_t smem = osc::kBuildStages * sizeof(osc::BuildStage<D>) +
-                      osc::kBuildStages * sizeof(uint64_t) + D::S * sizeof(double);
+int launch_build(osc_handle* h, cudaStream_t st, int env0, int n) {
+  constexpr int threads = osc::kBuildWarps * 32;
+  const size_t smem = osc::kBuildWarps * osc::kBuildStages * (sizeof(osc::BuildStage<D>) + sizeof(uint64_t)) +
+                      D::S * sizeof(double);
   auto kern = osc::build_qp_kernel<D>;
   OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   OSC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) per_sm = 1;
   int grid = h->sm_count * per_sm;
-  if (grid > h->n_envs) grid = h->n_envs;
-  kern<<<grid, threads, smem, st>>>(h->params, h->iJ, h->iBias, h->iTargets, h->dH, h->dF,
-                                    h->n_envs);
+  const int need = (n + osc::kBuildWarps - 1) / osc::kBuildWarps;
+  if (grid > need) grid = need;
+  const size_t e = (size_t)env0;
+  kern<<<grid, threads, smem, st>>>(h->params, h->iJ + e * D::S * D::NV, h->iBias + e * D::S,
+                                    h->iTargets + e * D::S, h->dH + e * D::NV * D::NV,
+                                    h->dF + e * D::NV, n);
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;
@@ -360,27 +423,36 @@ int launch_reset(osc_handle* h, cudaStream_t st) {
   return OSC_OK;
 }
 
-template <class D>
-int launch_solve(osc_handle* h, cudaStream_t st) {
-  constexpr int WARPS = solve_warps<D>();
+template <class D, int WARPS>
+int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
   static_assert(WARPS >= 1, "workspace does not fit in shared memory");
   const size_t smem = WARPS * sizeof(osc::Workspace<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::solve_kernel<D, WARPS>;
   OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = h->sm_count;
-  const int need = (h->n_envs + WARPS - 1) / WARPS;
+  const int need = (n + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
-  OSC_CUDA(h, cudaMemsetAsync(h->dCounter, 0, sizeof(int), st));
+  OSC_CUDA(h, cudaMemsetAsync(h->dCounter + counter, 0, sizeof(int), st));
+  const size_t e = (size_t)env0;
   osc::SolveArgs a;
-  a.M = h->iM; a.C = h->iC; a.J = h->iJ; a.mask = h->iMask; a.Hdv = h->dH; a.fdv = h->dF;
-  a.state = h->dState;
-  a.torque = h->dTorque; a.sol_x = h->dX; a.sol_y = h->dY;
-  a.pri_res = h->dPri; a.dua_res = h->dDua; a.rho = h->dRho;
-  a.iters = h->dIters; a.status = h->dStatus; a.counter = h->dCounter; a.n_envs = h->n_envs;
+  a.M = h->iM + e * D::NV * D::NV; a.C = h->iC + e * D::NV; a.J = h->iJ + e * D::S * D::NV;
+  a.mask = h->iMask + e * D::NC; a.Hdv = h->dH + e * D::NV * D::NV; a.fdv = h->dF + e * D::NV;
+  a.state = h->dState + e * D::STATE;
+  a.torque = h->dTorque + e * D::NU; a.sol_x = h->dX + e * D::N; a.sol_y = h->dY + e * D::M;
+  a.pri_res = h->dPri + e; a.dua_res = h->dDua + e; a.rho = h->dRho + e;
+  a.iters = h->dIters + e; a.status = h->dStatus + e; a.counter = h->dCounter + counter;
+  a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;
+}
+
+template <class D>
+int launch_solve(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  if (h->solve_warps_pref == 12 || solve_warps_hi<D>() == solve_warps_lo<D>())
+    return launch_solve_w<D, solve_warps_lo<D>()>(h, st, env0, n, counter);
+  return launch_solve_w<D, solve_warps_hi<D>()>(h, st, env0, n, counter);
 }
 
 #define OSC_DISPATCH(h, fn, ...)                                                    \
@@ -470,7 +542,14 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   }
   if ((ce = cudaMalloc((void**)&h->dIters, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   if ((ce = cudaMalloc((void**)&h->dStatus, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
-  if ((ce = cudaMalloc((void**)&h->dCounter, sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  h->n_counters = 64;
+  {
+    const char* e = getenv("OSC_B200_SOLVE_WARPS");
+    h->solve_warps_pref = e ? atoi(e) : 12;  // measured equal at 16 (128 regs, spills)
+  }
+  if ((ce = cudaMalloc((void**)&h->dCounter, h->n_counters * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");
+  if ((ce = cudaEventCreateWithFlags(&h->fence_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
   cudaMemset(h->dIters, 0, N * sizeof(int));
   cudaMemset(h->dStatus, 0, N * sizeof(int));
   h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
@@ -491,6 +570,9 @@ int osc_destroy(osc_handle* h) {
   if (h->dStatus) cudaFree(h->dStatus);
   if (h->dCounter) cudaFree(h->dCounter);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
+  if (h->fence_ev) cudaEventDestroy(h->fence_ev);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
   return OSC_OK;
 }
@@ -526,7 +608,7 @@ int osc_setup(osc_handle* h, void* stream) {
   if (check_handle(h)) return OSC_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   OSC_CUDA(h, cudaSetDevice(h->device));
-  int rc = OSC_DISPATCH(h, launch_build, h, st);
+  int rc = OSC_DISPATCH(h, launch_build, h, st, 0, h->n_envs);
   if (rc) return rc;
   rc = OSC_DISPATCH(h, launch_init_state, h, st);
   if (rc) return rc;
@@ -555,10 +637,10 @@ int osc_step(osc_handle* h, void* stream) {
     h->ev_used += 3;
     OSC_CUDA(h, cudaEventRecord(ev[0], st));
   }
-  int rc = OSC_DISPATCH(h, launch_build, h, st);
+  int rc = OSC_DISPATCH(h, launch_build, h, st, 0, h->n_envs);
   if (rc) return rc;
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
-  rc = OSC_DISPATCH(h, launch_solve, h, st);
+  rc = OSC_DISPATCH(h, launch_solve, h, st, 0, h->n_envs, 0);
   if (rc) return rc;
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[2], st));
   return OSC_OK;
@@ -660,13 +742,60 @@ int osc_sync(osc_handle* h, void* stream) {
 int osc_step_host(osc_handle* h, const double* M, const double* C, const double* J,
                   const double* bias, const double* targets, const double* mask, double* torque,
                   void* stream) {
-  int rc = osc_upload(h, M, C, J, bias, targets, mask, stream);
-  if (rc) return rc;
-  if ((rc = osc_step(h, stream))) return rc;
-  if ((rc = osc_download(h, torque, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                         stream)))
-    return rc;
-  return osc_sync(h, stream);
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!h->setup_done) {
+    h->err = "osc_step_host: osc_setup has not been called";
+    return OSC_ERR_STATE;
+  }
+  if (!M || !C || !J || !bias || !targets || !mask || !torque) {
+    h->err = "osc_step_host: null host buffer";
+    return OSC_ERR_INVALID;
+  }
+  if (h->iM != h->dM || h->iJ != h->dJ) {
+    h->err = "osc_step_host: inputs are bound to caller-owned device memory (osc_bind_device_inputs)";
+    return OSC_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  // Software pipeline over chunks of environments: the H2D copy of chunk c+1 (copy stream)
+  // overlaps build+solve of chunk c (caller's stream); torques return per chunk.
+  const int N = h->n_envs;
+  int chunk = 2048;
+  int nchunks = (N + chunk - 1) / chunk;
+  if (nchunks > h->n_counters) {
+    nchunks = h->n_counters;
+    chunk = (N + nchunks - 1) / nchunks;
+  }
+  while ((int)h->chunk_ev.size() < nchunks) {
+    cudaEvent_t e;
+    OSC_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->chunk_ev.push_back(e);
+  }
+  // the copy stream may not overwrite inputs still being read by earlier work on `st`
+  OSC_CUDA(h, cudaEventRecord(h->fence_ev, st));
+  OSC_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->fence_ev, 0));
+  const size_t B = sizeof(double);
+  const size_t nv = h->nv, s = h->s, nc = h->nc, nu = h->nu;
+  for (int c = 0; c < nchunks; ++c) {
+    const size_t e0 = (size_t)c * chunk;
+    const size_t n = (size_t)((e0 + chunk <= (size_t)N) ? chunk : N - e0);
+    cudaStream_t cs = h->copy_stream;
+    OSC_CUDA(h, cudaMemcpyAsync(h->dJ + e0 * s * nv, J + e0 * s * nv, n * s * nv * B, cudaMemcpyHostToDevice, cs));
+    OSC_CUDA(h, cudaMemcpyAsync(h->dM + e0 * nv * nv, M + e0 * nv * nv, n * nv * nv * B, cudaMemcpyHostToDevice, cs));
+    OSC_CUDA(h, cudaMemcpyAsync(h->dBias + e0 * s, bias + e0 * s, n * s * B, cudaMemcpyHostToDevice, cs));
+    OSC_CUDA(h, cudaMemcpyAsync(h->dTargets + e0 * s, targets + e0 * s, n * s * B, cudaMemcpyHostToDevice, cs));
+    OSC_CUDA(h, cudaMemcpyAsync(h->dC + e0 * nv, C + e0 * nv, n * nv * B, cudaMemcpyHostToDevice, cs));
+    OSC_CUDA(h, cudaMemcpyAsync(h->dMask + e0 * nc, mask + e0 * nc, n * nc * B, cudaMemcpyHostToDevice, cs));
+    OSC_CUDA(h, cudaEventRecord(h->chunk_ev[c], cs));
+    OSC_CUDA(h, cudaStreamWaitEvent(st, h->chunk_ev[c], 0));
+    int rc = OSC_DISPATCH(h, launch_build, h, st, (int)e0, (int)n);
+    if (rc) return rc;
+    rc = OSC_DISPATCH(h, launch_solve, h, st, (int)e0, (int)n, c);
+    if (rc) return rc;
+    OSC_CUDA(h, cudaMemcpyAsync(torque + e0 * nu, h->dTorque + e0 * nu, n * nu * B, cudaMemcpyDeviceToHost, st));
+  }
+  OSC_CUDA(h, cudaStreamSynchronize(st));
+  return OSC_OK;
 }
 
 long long osc_kernel_launches(const osc_handle* h) { return h ? h->launches : 0; }

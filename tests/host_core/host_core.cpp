@@ -32,12 +32,11 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
   std::memcpy(ws->Ae, M, sizeof(double) * D::NV * D::NV);
   std::memcpy(ws->Pdv, H, sizeof(H));
   std::memcpy(ws->scratch, J + D::JC0 * D::NV, sizeof(double) * D::NZ * D::NV);
-  std::memcpy(ws->x, state, sizeof(double) * D::STATE);
+  std::memcpy(ws->land, state, sizeof(double) * D::STATE);
   std::memcpy(ws->Cv, C, sizeof(double) * D::NV);
   std::memcpy(ws->fv, f, sizeof(f));
   std::memcpy(ws->maskv, mask, sizeof(double) * D::NC);
-  osc::Result r = Core::step(*ws, p, 0, x, y, torque);
-  std::memcpy(state, ws->x, sizeof(double) * D::STATE);
+  osc::Result r = Core::step(*ws, p, 0, f, x, y, torque, state);
   info_i[0] = r.iter;
   info_i[1] = r.status;
   info_i[2] = r.rho_updates;
