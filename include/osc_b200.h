@@ -141,6 +141,10 @@ int osc_reset_warm_start(osc_handle *h, void *stream);
 int osc_download(osc_handle *h, double *torque, double *solution, double *dual, int *iters,
                  int *status, double *pri_res, double *dua_res, double *rho, void *stream);
 int osc_sync(osc_handle *h, void *stream);
+/* The objective the last osc_setup/osc_step built: H's dv block [n_envs][nv*nv] and f's dv
+ * part [n_envs][nv] (OptimizationData.H / .f, containers.h:23-25; all other entries of H and f
+ * are the constants 2 w_reg (+2 w_torque on u) and 0).  Inspection / tests. */
+int osc_download_objective(osc_handle *h, double *H_dv, double *f_dv, void *stream);
 
 /* update_state/update_taskspace_targets + control step + get_torque_command for a
  * whole batch with HOST buffers: upload, step, download torques, synchronise. */

@@ -75,10 +75,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // ---------------------------------------------------------------------------
 // K2: objective build.  One warp per environment; every warp owns a 2-stage ring of TMA
-// bulk copies (J, bias, targets of one environment per stage).  H = 2 J'WJ + 2 w_reg I is
-// produced in 2x2 register tiles of its lower triangle (one tile per lane, two 16-byte
-// shared-memory loads feed four FMAs per weighted row), f = 2 J'W(bias - t) by the
-// remaining lanes, four entries each.  Rows with zero weight are skipped (warp-uniform).
+// bulk copies (J, bias, targets of one environment per stage).
+//   H = 2 J'WJ + 2 w_reg I   is a small GEMM  sum_k (w_k J_k)' J_k  with K = 6 ns rows, and
+//   f = 2 J'W(bias - t)      is the same product against one more column r = bias - t,
+// so both run on the FP64 tensor cores: mma.sync m8n8k4 (DMMA), 8x8 output tiles of the
+// lower triangle of H plus one 8-wide tile per row block whose first column is f.
+// Per 4 rows of J a lane loads one element per 8-column block (A and B fragments of a
+// tile are the same J entries), scales the A copy by the row weight and issues the MMAs.
 // ---------------------------------------------------------------------------
 template <class D>
 struct BuildStage {
@@ -89,22 +92,29 @@ struct BuildStage {
 constexpr int kBuildStages = 2;
 constexpr int kBuildWarps = 4;
 
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 template <class D>
 __global__ void __launch_bounds__(kBuildWarps * 32)
 build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
                 const double* __restrict__ bias, const double* __restrict__ targets,
                 double* __restrict__ Hdv, double* __restrict__ fdv, int n_envs) {
   constexpr int NV = D::NV, S = D::S, NS = D::NS;
-  constexpr int NT = NV / 2;                 // tiles per side
-  constexpr int NTILE = NT * (NT + 1) / 2;   // lower-triangle 2x2 tiles
-  constexpr int NFG = (NV + 3) / 4;          // groups of 4 entries of f
-  constexpr int NITEM = NTILE + NFG;
+  constexpr int NB8 = (NV + 7) / 8;              // 8-column blocks of J
+  constexpr int NTILE = NB8 * (NB8 + 1) / 2;     // lower-triangle 8x8 tiles of H
+  constexpr int KSTEPS = (S + 3) / 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BuildStage<D>* stages = reinterpret_cast<BuildStage<D>*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kBuildWarps * kBuildStages * sizeof(BuildStage<D>));
-  double* w_row = reinterpret_cast<double*>(bars + kBuildWarps * kBuildStages);
+  double* w_row = reinterpret_cast<double*>(bars + kBuildWarps * kBuildStages);  // 4*KSTEPS, zero padded
+  int* t_idx = reinterpret_cast<int*>(w_row + 4 * KSTEPS);  // index into targets of row k
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;  // MMA fragment coordinates
   BuildStage<D>* my = stages + warp * kBuildStages;
   uint64_t* mybar = bars + warp * kBuildStages;
   constexpr uint32_t kBytes = sizeof(BuildStage<D>);
@@ -119,7 +129,14 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
     for (int s = 0; s < kBuildWarps * kBuildStages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
-  for (int k = threadIdx.x; k < S; k += blockDim.x) w_row[k] = p.w_row[k];
+  for (int k = threadIdx.x; k < 4 * KSTEPS; k += blockDim.x) {
+    w_row[k] = k < S ? p.w_row[k] : 0.0;
+    // row k of ddx: site (k mod 3NS)/3, translational rows read targets cols 0-2,
+    // rotational rows cols 3-5 (autogen.py:163,173-177)
+    const int kc = k < S ? k : S - 1;
+    const int kr = (kc < 3 * NS) ? kc : kc - 3 * NS;
+    t_idx[k] = (kr / 3) * 6 + (kr % 3) + ((kc < 3 * NS) ? 0 : 3);
+  }
   __syncthreads();
   const int stride = gridDim.x * kBuildWarps;
   const int env0 = blockIdx.x * kBuildWarps + warp;
@@ -133,69 +150,64 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
     const int stage = it % kBuildStages;
     mbar_wait(&mybar[stage], (it / kBuildStages) & 1);
     const BuildStage<D>& st = my[stage];
-    for (int item = lane; item < NITEM; item += 32) {
-      if (item < NTILE) {
-        int ta = 0, t = item;
-        while (t > ta) {
-          t -= ta + 1;
-          ++ta;
-        }
-        const int a = 2 * ta, b = 2 * t;  // tile rows a,a+1 ; cols b,b+1 ; b <= a
-        double h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+    double acc[NTILE][2], facc[NB8][2];
+#pragma unroll
+    for (int q = 0; q < NTILE; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NB8; ++q) facc[q][0] = facc[q][1] = 0.0;
 #pragma unroll 2
-        for (int k = 0; k < S; ++k) {
-          const double wk = w_row[k];
-          if (wk != 0.0) {
-            const double2 ja = *reinterpret_cast<const double2*>(&st.J[k * NV + a]);
-            const double2 jb = *reinterpret_cast<const double2*>(&st.J[k * NV + b]);
-            const double wa0 = wk * ja.x, wa1 = wk * ja.y;
-            h00 += wa0 * jb.x;
-            h01 += wa0 * jb.y;
-            h10 += wa1 * jb.x;
-            h11 += wa1 * jb.y;
-          }
-        }
-        h00 *= 2.0; h01 *= 2.0; h10 *= 2.0; h11 *= 2.0;
-        double* H = Hdv + (size_t)env * NV * NV;
-        if (a == b) {
-          // diagonal tile: h01 and h10 were accumulated as (w Ja)Jb with the operand order
-          // of the lower-triangle entry (a+1, a); mirror that one like the reference's H
-          h00 += two_wreg;
-          h11 += two_wreg;
-          *reinterpret_cast<double2*>(&H[a * NV + a]) = make_double2(h00, h10);
-          *reinterpret_cast<double2*>(&H[(a + 1) * NV + a]) = make_double2(h10, h11);
-        } else {
-          *reinterpret_cast<double2*>(&H[a * NV + b]) = make_double2(h00, h01);
-          *reinterpret_cast<double2*>(&H[(a + 1) * NV + b]) = make_double2(h10, h11);
-          *reinterpret_cast<double2*>(&H[b * NV + a]) = make_double2(h00, h10);
-          *reinterpret_cast<double2*>(&H[(b + 1) * NV + a]) = make_double2(h01, h11);
-        }
-      } else {
-        const int a = 4 * (item - NTILE);
-        double g0 = 0, g1 = 0, g2 = 0, g3 = 0;
-        for (int k = 0; k < S; ++k) {
-          const double wk = w_row[k];
-          if (wk != 0.0) {
-            const int kr = (k < 3 * NS) ? k : k - 3 * NS;
-            const int site = kr / 3, kk = kr - 3 * site;
-            const double r = st.bias[k] - st.targets[site * 6 + ((k < 3 * NS) ? kk : 3 + kk)];
-            const double* jr = &st.J[k * NV + a];
-            g0 += (wk * jr[0]) * r;
-            g1 += (wk * jr[1]) * r;
-            if (a + 2 < NV) {
-              g2 += (wk * jr[2]) * r;
-              g3 += (wk * jr[3]) * r;
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const int k = 4 * ks + t;            // this lane's row of J inside the k-step
+      const int kc = k < S ? k : S - 1;    // clamp (weight is 0 beyond S)
+      const double wk = w_row[k];
+      double jb[NB8], ja[NB8];
+#pragma unroll
+      for (int q = 0; q < NB8; ++q) {
+        const int col = 8 * q + g;
+        jb[q] = col < NV ? st.J[kc * NV + col] : 0.0;
+        ja[q] = wk * jb[q];
+      }
+      const double r = (g == 0) ? (st.bias[kc] - st.targets[t_idx[k]]) : 0.0;
+      int tile = 0;
+#pragma unroll
+      for (int mi = 0; mi < NB8; ++mi) {
+#pragma unroll
+        for (int ni = 0; ni <= mi; ++ni, ++tile) dmma_m8n8k4(acc[tile][0], acc[tile][1], ja[mi], jb[ni]);
+        dmma_m8n8k4(facc[mi][0], facc[mi][1], ja[mi], r);
+      }
+    }
+    // C fragment: lane holds C[g][2t], C[g][2t+1] of every tile
+    double* H = Hdv + (size_t)env * NV * NV;
+    int tile = 0;
+#pragma unroll
+    for (int mi = 0; mi < NB8; ++mi) {
+      const int row = 8 * mi + g;
+#pragma unroll
+      for (int ni = 0; ni <= mi; ++ni, ++tile) {
+        const int col = 8 * ni + 2 * t;
+        double v0 = 2.0 * acc[tile][0], v1 = 2.0 * acc[tile][1];
+        if (row < NV && col < NV) {
+          if (mi == ni) {
+            // keep the symmetric matrix exactly symmetric: the lower-triangle value is used
+            // for both (i,j) and (j,i), like the reference's mirrored Hessian
+            if (col <= row) {
+              if (col == row) v0 += two_wreg;
+              H[row * NV + col] = v0;
+              if (col != row) H[col * NV + row] = v0;
             }
+            if (col + 1 <= row) {
+              if (col + 1 == row) v1 += two_wreg;
+              H[row * NV + col + 1] = v1;
+              if (col + 1 != row) H[(col + 1) * NV + row] = v1;
+            }
+          } else {
+            *reinterpret_cast<double2*>(&H[row * NV + col]) = make_double2(v0, v1);
+            H[col * NV + row] = v0;
+            H[(col + 1) * NV + row] = v1;
           }
-        }
-        double* f = fdv + (size_t)env * NV + a;
-        f[0] = 2.0 * g0;
-        f[1] = 2.0 * g1;
-        if (a + 2 < NV) {
-          f[2] = 2.0 * g2;
-          f[3] = 2.0 * g3;
         }
       }
+      if (t == 0 && row < NV) fdv[(size_t)env * NV + row] = 2.0 * facc[mi][0];
     }
     __syncwarp();  // the whole warp is done reading this stage
     if (lane == 0) {
@@ -379,8 +391,9 @@ constexpr int solve_warps_lo() { return max_solve_warps<D>() > 12 ? 12 : max_sol
 template <class D>
 int launch_build(osc_handle* h, cudaStream_t st, int env0, int n) {
   constexpr int threads = osc::kBuildWarps * 32;
+  constexpr int kRows = 4 * ((D::S + 3) / 4);
   const size_t smem = osc::kBuildWarps * osc::kBuildStages * (sizeof(osc::BuildStage<D>) + sizeof(uint64_t)) +
-                      D::S * sizeof(double);
+                      kRows * (sizeof(double) + sizeof(int));
   auto kern = osc::build_qp_kernel<D>;
   OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -729,6 +742,16 @@ int osc_download(osc_handle* h, double* torque, double* solution, double* dual, 
   if (pri_res) OSC_CUDA(h, cudaMemcpyAsync(pri_res, h->dPri, N * B, cudaMemcpyDeviceToHost, st));
   if (dua_res) OSC_CUDA(h, cudaMemcpyAsync(dua_res, h->dDua, N * B, cudaMemcpyDeviceToHost, st));
   if (rho) OSC_CUDA(h, cudaMemcpyAsync(rho, h->dRho, N * B, cudaMemcpyDeviceToHost, st));
+  return OSC_OK;
+}
+
+int osc_download_objective(osc_handle* h, double* H_dv, double* f_dv, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  const size_t N = (size_t)h->n_envs, B = sizeof(double);
+  if (H_dv) OSC_CUDA(h, cudaMemcpyAsync(H_dv, h->dH, N * h->nv * h->nv * B, cudaMemcpyDeviceToHost, st));
+  if (f_dv) OSC_CUDA(h, cudaMemcpyAsync(f_dv, h->dF, N * h->nv * B, cudaMemcpyDeviceToHost, st));
   return OSC_OK;
 }
 

@@ -26,7 +26,7 @@ EXPORTS = (
     "osc_get_device_buffers", "osc_upload", "osc_setup", "osc_step", "osc_reset_warm_start",
     "osc_download", "osc_sync", "osc_step_host", "osc_kernel_launches",
     "osc_measure_dfma_tflops", "osc_host_alloc", "osc_host_free", "osc_bind_device_inputs",
-    "osc_timing_enable", "osc_timing_read",
+    "osc_timing_enable", "osc_timing_read", "osc_download_objective",
 )
 
 
@@ -90,6 +90,7 @@ def load():
     L.osc_reset_warm_start.argtypes = [vp, vp]
     L.osc_download.argtypes = [vp] + [vp] * 8 + [vp]
     L.osc_sync.argtypes = [vp, vp]
+    L.osc_download_objective.argtypes = [vp, vp, vp, vp]
     L.osc_step_host.argtypes = [vp] + [vp] * 7 + [vp]
     L.osc_kernel_launches.argtypes = [vp]
     L.osc_kernel_launches.restype = C.c_longlong
@@ -246,6 +247,15 @@ class BatchedOSC:
             out["dua_res"].ctypes.data, out["rho"].ctypes.data, stream), "osc_download")
         self.sync(stream)
         return out
+
+    def objective(self, stream=None):
+        """H's dv block [N, nv, nv] and f's dv part [N, nv] as built by the last setup/step."""
+        H = np.empty((self.n_envs, self.spec.nv, self.spec.nv))
+        f = np.empty((self.n_envs, self.spec.nv))
+        self._check(self.L.osc_download_objective(self.h, H.ctypes.data, f.ctypes.data, stream),
+                    "osc_download_objective")
+        self.sync(stream)
+        return H, f
 
     def torques(self, stream=None) -> np.ndarray:
         tq = np.empty((self.n_envs, self.spec.nu))

@@ -239,3 +239,25 @@ def test_cpp_controller_class_drop_in(oracle, tmp_path):
         assert (np.abs(tq - o["torque"][0]) <= tol).all(), (preset, tq, o["torque"][0])
         tq2 = np.array([float(v) for v in lines["TORQUE_THREAD"]])
         assert np.isfinite(tq2).all() and np.abs(tq2 - tq).max() < 1.0 + 0.1 * np.abs(tq).max()
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_true_tumbling_mjjoint", "tumbling"),
+                                           ("walter_sr", "standing"),
+                                           ("unitree_go2", "go2_standing")])
+def test_build_kernel_objective_matches_oracle(oracle, preset, config):
+    """H (dv block) and f from the tensor-core build kernel vs the oracle's closed forms:
+    FP64 round-off only (different summation order), exactly symmetric, ragged batch size."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    n_envs = 301  # not a multiple of the warps per CTA
+    inp = ob.synth.make_inputs(spec, n_envs, config)
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(inp)
+    H, f = g.objective()
+    assert np.array_equal(H, H.transpose(0, 2, 1))
+    for e in (0, 1, 150, 300):
+        Ho, fo, *_ = oracle.build_qp(spec, *[inp[k][e] for k in ("M", "C", "J", "bias", "targets", "mask")])
+        sc = np.abs(Ho[:spec.nv, :spec.nv]).max()
+        np.testing.assert_allclose(H[e], Ho[:spec.nv, :spec.nv], rtol=1e-12, atol=1e-12 * sc)
+        np.testing.assert_allclose(f[e], fo[:spec.nv], rtol=1e-11, atol=1e-12 * np.abs(fo).max())
