@@ -79,7 +79,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 //   H = 2 J'WJ + 2 w_reg I   is a small GEMM  sum_k (w_k J_k)' J_k  with K = 6 ns rows, and
 //   f = 2 J'W(bias - t)      is the same product against one more column r = bias - t,
 // so both run on the FP64 tensor cores: mma.sync m8n8k4 (DMMA), 8x8 output tiles of the
-// lower triangle of H plus one 8-wide tile per row block whose first column is f.
+// lower triangle of H.  nv is not a multiple of 8, so the last 8-column block of J has
+// zero padding: r is placed in padding column nv, which makes row (nv mod 8) of the last
+// tile row equal to f/2 -- f costs no extra MMA.
 // Per 4 rows of J a lane loads one element per 8-column block (A and B fragments of a
 // tile are the same J entries), scales the A copy by the row weight and issues the MMAs.
 // ---------------------------------------------------------------------------
@@ -107,6 +109,7 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
   constexpr int NB8 = (NV + 7) / 8;              // 8-column blocks of J
   constexpr int NTILE = NB8 * (NB8 + 1) / 2;     // lower-triangle 8x8 tiles of H
   constexpr int KSTEPS = (S + 3) / 4;
+  static_assert(NV % 8 != 0, "f rides in the zero padding of the last 8-column block");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BuildStage<D>* stages = reinterpret_cast<BuildStage<D>*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kBuildWarps * kBuildStages * sizeof(BuildStage<D>));
@@ -150,11 +153,15 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
     const int stage = it % kBuildStages;
     mbar_wait(&mybar[stage], (it / kBuildStages) & 1);
     const BuildStage<D>& st = my[stage];
-    double acc[NTILE][2], facc[NB8][2];
+    // r = bias - t, in place over the staged bias (t re-ordered [translational ; rotational])
+    {
+      double* b = const_cast<double*>(st.bias);
+      for (int k = lane; k < S; k += 32) b[k] = b[k] - st.targets[t_idx[k]];
+      __syncwarp();
+    }
+    double acc[NTILE][2];
 #pragma unroll
     for (int q = 0; q < NTILE; ++q) acc[q][0] = acc[q][1] = 0.0;
-#pragma unroll
-    for (int q = 0; q < NB8; ++q) facc[q][0] = facc[q][1] = 0.0;
 #pragma unroll 2
     for (int ks = 0; ks < KSTEPS; ++ks) {
       const int k = 4 * ks + t;            // this lane's row of J inside the k-step
@@ -164,17 +171,20 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
 #pragma unroll
       for (int q = 0; q < NB8; ++q) {
         const int col = 8 * q + g;
-        jb[q] = col < NV ? st.J[kc * NV + col] : 0.0;
+        if (q < NB8 - 1) {
+          jb[q] = st.J[kc * NV + col];
+        } else {
+          // last block: columns < nv from J, column nv carries r, the rest is zero
+          const double* src = col < NV ? &st.J[kc * NV + col] : &st.bias[kc];
+          jb[q] = col <= NV ? *src : 0.0;
+        }
         ja[q] = wk * jb[q];
       }
-      const double r = (g == 0) ? (st.bias[kc] - st.targets[t_idx[k]]) : 0.0;
       int tile = 0;
 #pragma unroll
-      for (int mi = 0; mi < NB8; ++mi) {
+      for (int mi = 0; mi < NB8; ++mi)
 #pragma unroll
         for (int ni = 0; ni <= mi; ++ni, ++tile) dmma_m8n8k4(acc[tile][0], acc[tile][1], ja[mi], jb[ni]);
-        dmma_m8n8k4(facc[mi][0], facc[mi][1], ja[mi], r);
-      }
     }
     // C fragment: lane holds C[g][2t], C[g][2t+1] of every tile
     double* H = Hdv + (size_t)env * NV * NV;
@@ -207,7 +217,16 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
           }
         }
       }
-      if (t == 0 && row < NV) fdv[(size_t)env * NV + row] = 2.0 * facc[mi][0];
+    }
+    // f/2 = row (nv mod 8) of the last tile row: sum_k (w_k r_k) J[k][col]
+    if (g == NV % 8) {
+#pragma unroll
+      for (int ni = 0; ni < NB8; ++ni) {
+        const int q = (NB8 - 1) * NB8 / 2 + ni;
+        const int col = 8 * ni + 2 * t;
+        if (col < NV) fdv[(size_t)env * NV + col] = 2.0 * acc[q][0];
+        if (col + 1 < NV) fdv[(size_t)env * NV + col + 1] = 2.0 * acc[q][1];
+      }
     }
     __syncwarp();  // the whole warp is done reading this stage
     if (lane == 0) {
@@ -353,6 +372,8 @@ struct osc_handle {
   cudaEvent_t fence_ev;
   int n_counters;
   int solve_warps_pref;
+  int build_grid_max;   // resident CTAs of build_qp_kernel on the device
+  bool kernels_ready;
   // optional per-kernel timing
   bool timing;
   std::vector<cudaEvent_t> ev;  // 3 events per recorded step
@@ -395,11 +416,14 @@ int launch_build(osc_handle* h, cudaStream_t st, int env0, int n) {
   const size_t smem = osc::kBuildWarps * osc::kBuildStages * (sizeof(osc::BuildStage<D>) + sizeof(uint64_t)) +
                       kRows * (sizeof(double) + sizeof(int));
   auto kern = osc::build_qp_kernel<D>;
-  OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  OSC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) per_sm = 1;
-  int grid = h->sm_count * per_sm;
+  if (!h->kernels_ready) {
+    OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    OSC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    h->build_grid_max = h->sm_count * per_sm;
+  }
+  int grid = h->build_grid_max;
   const int need = (n + osc::kBuildWarps - 1) / osc::kBuildWarps;
   if (grid > need) grid = need;
   const size_t e = (size_t)env0;
@@ -441,7 +465,8 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   static_assert(WARPS >= 1, "workspace does not fit in shared memory");
   const size_t smem = WARPS * sizeof(osc::Workspace<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::solve_kernel<D, WARPS>;
-  OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!h->kernels_ready)
+    OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = h->sm_count;
   const int need = (n + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
@@ -569,6 +594,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   h->iMask = h->dMask;
   h->timing = false;
   h->ev_used = 0;
+  h->kernels_ready = false;
+  h->build_grid_max = h->sm_count;
   *out = h;
   return OSC_OK;
 }
@@ -655,6 +682,7 @@ int osc_step(osc_handle* h, void* stream) {
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
   rc = OSC_DISPATCH(h, launch_solve, h, st, 0, h->n_envs, 0);
   if (rc) return rc;
+  h->kernels_ready = true;  // function attributes / occupancy are set from here on
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[2], st));
   return OSC_OK;
 }
@@ -817,6 +845,7 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
     if (rc) return rc;
     OSC_CUDA(h, cudaMemcpyAsync(torque + e0 * nu, h->dTorque + e0 * nu, n * nu * B, cudaMemcpyDeviceToHost, st));
   }
+  h->kernels_ready = true;
   OSC_CUDA(h, cudaStreamSynchronize(st));
   return OSC_OK;
 }
