@@ -29,6 +29,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "operational-space-control_b200", "python"))
+# stdout carries exactly one JSON line: keep NCCL's version banner off it
+os.environ["NCCL_DEBUG"] = os.environ.get("OSC_BENCH_NCCL_DEBUG", "WARN")
 
 import numpy as np  # noqa: E402
 
