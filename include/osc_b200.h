@@ -173,6 +173,12 @@ typedef struct {
 int osc_timing_enable(osc_handle *h, int on);
 int osc_timing_read(osc_handle *h, osc_kernel_times *out);
 
+/* How many environment-steps so far took the reference's sparsity-change path
+ * (update_optimization :571-584: UpdateObjectiveAndConstraintMatrices rejected the new
+ * pattern -> solver re-Init with rho reset + SetWarmStart(solution, dual_solution)).
+ * Synchronises `stream`. */
+int osc_reinit_count(osc_handle *h, int *count, void *stream);
+
 /* number of kernels launched by this handle so far (bench bookkeeping) */
 long long osc_kernel_launches(const osc_handle *h);
 

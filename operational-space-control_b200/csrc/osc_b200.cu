@@ -239,19 +239,46 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
 // ---------------------------------------------------------------------------
 // set_up_optimization(): Init state
 // ---------------------------------------------------------------------------
+// One warp per environment: zero iterates, previous linear cost = f, rho0, flag, and the
+// sparsity signature of the data the "workspace" is initialised with.
 template <class D>
 __global__ void init_state_kernel(double* __restrict__ state, const double* __restrict__ fdv,
-                                  double rho0, int n_envs) {
-  constexpr int ST = D::STATE, QOFF = D::N + 2 * D::M;
-  const size_t total = (size_t)n_envs * ST;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int env = (int)(i / ST), k = (int)(i - (size_t)env * ST);
-    double v = 0.0;
-    if (k >= QOFF && k < QOFF + D::NV) v = fdv[(size_t)env * D::NV + (k - QOFF)];
-    else if (k == QOFF + D::NV) v = rho0;
-    else if (k == QOFF + D::NV + 1) v = 1.0;
-    state[i] = v;
+                                  const double* __restrict__ Hdv, const double* __restrict__ M,
+                                  const double* __restrict__ J, double rho0, int n_envs) {
+  constexpr int NV = D::NV, QOFF = D::N + 2 * D::M;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; env < n_envs; env += warps) {
+    double* st = state + (size_t)env * D::STATE;
+    for (int k = lane; k < QOFF; k += 32) st[k] = 0.0;
+    for (int k = lane; k < NV; k += 32) st[QOFF + k] = fdv[(size_t)env * NV + k];
+    if (lane == 0) {
+      st[QOFF + NV] = rho0;
+      st[QOFF + NV + 1] = 1.0;
+    }
+    const double* H = Hdv + (size_t)env * NV * NV;
+    const double* Mm = M + (size_t)env * NV * NV;
+    const double* Jc = J + ((size_t)env * D::S + D::JC0) * NV;
+    auto bit = [&](int b) -> bool {
+      if (b < D::NTRI) {
+        int i = 0, j = b;
+        while (j > i) {
+          j -= i + 1;
+          ++i;
+        }
+        return H[i * NV + j] != 0.0;
+      }
+      b -= D::NTRI;
+      if (b < NV * NV) return Mm[b] != 0.0;
+      b -= NV * NV;
+      if (b < NV * D::NZ) return Jc[b] != 0.0;
+      return false;
+    };
+    for (int q = 0; q < D::SIG; ++q) {
+      const unsigned lo = __ballot_sync(0xffffffffu, bit(64 * q + lane));
+      const unsigned hi = __ballot_sync(0xffffffffu, bit(64 * q + 32 + lane));
+      if (lane == 0) st[D::SIG0 + q] = __longlong_as_double(((long long)hi << 32) | (long long)lo);
+    }
   }
 }
 
@@ -275,6 +302,7 @@ struct SolveArgs {
   double *torque, *sol_x, *sol_y, *pri_res, *dua_res, *rho;
   int *iters, *status;
   int* counter;
+  int* reinits;
   int n_envs;
 };
 
@@ -326,6 +354,7 @@ solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
       a.pri_res[env] = r.pri_res;
       a.dua_res[env] = r.dua_res;
       a.rho[env] = r.rho;
+      if (r.reinit) atomicAdd(a.reinits, 1);
     }
     __syncwarp();
   }
@@ -438,11 +467,10 @@ int launch_build(osc_handle* h, cudaStream_t st, int env0, int n) {
 template <class D>
 int launch_init_state(osc_handle* h, cudaStream_t st) {
   const int threads = 256;
-  const size_t total = (size_t)h->n_envs * D::STATE;
-  int grid = (int)((total + threads - 1) / threads);
+  int grid = (h->n_envs + 7) / 8;
   if (grid > h->sm_count * 8) grid = h->sm_count * 8;
-  osc::init_state_kernel<D><<<grid, threads, 0, st>>>(h->dState, h->dF, h->params.rho0,
-                                                      h->n_envs);
+  osc::init_state_kernel<D><<<grid, threads, 0, st>>>(h->dState, h->dF, h->dH, h->iM, h->iJ,
+                                                      h->params.rho0, h->n_envs);
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;
@@ -479,6 +507,7 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   a.torque = h->dTorque + e * D::NU; a.sol_x = h->dX + e * D::N; a.sol_y = h->dY + e * D::M;
   a.pri_res = h->dPri + e; a.dua_res = h->dDua + e; a.rho = h->dRho + e;
   a.iters = h->dIters + e; a.status = h->dStatus + e; a.counter = h->dCounter + counter;
+  a.reinits = h->dCounter + h->n_counters;  // one extra slot after the work counters
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
@@ -585,9 +614,10 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
     const char* e = getenv("OSC_B200_SOLVE_WARPS");
     h->solve_warps_pref = e ? atoi(e) : 12;  // measured equal at 16 (128 regs, spills)
   }
-  if ((ce = cudaMalloc((void**)&h->dCounter, h->n_counters * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  if ((ce = cudaMalloc((void**)&h->dCounter, (h->n_counters + 1) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");
   if ((ce = cudaEventCreateWithFlags(&h->fence_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
+  cudaMemset(h->dCounter, 0, (h->n_counters + 1) * sizeof(int));
   cudaMemset(h->dIters, 0, N * sizeof(int));
   cudaMemset(h->dStatus, 0, N * sizeof(int));
   h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
@@ -851,6 +881,15 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
 }
 
 long long osc_kernel_launches(const osc_handle* h) { return h ? h->launches : 0; }
+
+int osc_reinit_count(osc_handle* h, int* count, void* stream) {
+  if (check_handle(h) || !count) return OSC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  OSC_CUDA(h, cudaMemcpyAsync(count, h->dCounter + h->n_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+  OSC_CUDA(h, cudaStreamSynchronize(st));
+  return OSC_OK;
+}
 
 int osc_measure_dfma_tflops(int device, double* tflops) {
   if (!tflops) return OSC_ERR_INVALID;

@@ -26,7 +26,7 @@ EXPORTS = (
     "osc_get_device_buffers", "osc_upload", "osc_setup", "osc_step", "osc_reset_warm_start",
     "osc_download", "osc_sync", "osc_step_host", "osc_kernel_launches",
     "osc_measure_dfma_tflops", "osc_host_alloc", "osc_host_free", "osc_bind_device_inputs",
-    "osc_timing_enable", "osc_timing_read", "osc_download_objective",
+    "osc_timing_enable", "osc_timing_read", "osc_download_objective", "osc_reinit_count",
 )
 
 
@@ -90,6 +90,7 @@ def load():
     L.osc_reset_warm_start.argtypes = [vp, vp]
     L.osc_download.argtypes = [vp] + [vp] * 8 + [vp]
     L.osc_sync.argtypes = [vp, vp]
+    L.osc_reinit_count.argtypes = [vp, ip, vp]
     L.osc_download_objective.argtypes = [vp, vp, vp, vp]
     L.osc_step_host.argtypes = [vp] + [vp] * 7 + [vp]
     L.osc_kernel_launches.argtypes = [vp]
@@ -283,6 +284,12 @@ class BatchedOSC:
         t = CKernelTimes()
         self._check(self.L.osc_timing_read(self.h, C.byref(t)), "osc_timing_read")
         return t
+
+    def reinit_count(self, stream=None) -> int:
+        """Environment-steps that took the sparsity-change (re-Init) path so far."""
+        c = C.c_int(0)
+        self._check(self.L.osc_reinit_count(self.h, C.byref(c), stream), "osc_reinit_count")
+        return c.value
 
     @property
     def kernel_launches(self) -> int:

@@ -32,6 +32,16 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
   std::memcpy(ws->Ae, M, sizeof(double) * D::NV * D::NV);
   std::memcpy(ws->Pdv, H, sizeof(H));
   std::memcpy(ws->scratch, J + D::JC0 * D::NV, sizeof(double) * D::NZ * D::NV);
+  if (!x) {
+    // osc_setup (init_state_kernel): cold iterates, previous linear cost = f, rho0,
+    // initialised flag, sparsity signature of the set-up data
+    std::memset(state, 0, sizeof(double) * D::STATE);
+    std::memcpy(state + D::N + 2 * D::M, f, sizeof(f));
+    state[D::N + 2 * D::M + D::NV] = p.rho0;
+    state[D::N + 2 * D::M + D::NV + 1] = 1.0;
+    for (int q = 0; q < D::SIG; ++q) state[D::SIG0 + q] = Core::as_f64(Core::sig_word(*ws, q, 0));
+    return 0;
+  }
   std::memcpy(ws->land, state, sizeof(double) * D::STATE);
   std::memcpy(ws->Cv, C, sizeof(double) * D::NV);
   std::memcpy(ws->fv, f, sizeof(f));
@@ -40,6 +50,7 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
   info_i[0] = r.iter;
   info_i[1] = r.status;
   info_i[2] = r.rho_updates;
+  info_i[3] = r.reinit;
   info_d[0] = r.pri_res;
   info_d[1] = r.dua_res;
   info_d[2] = r.rho;
@@ -55,8 +66,10 @@ extern "C" int osc_core_host_state_size(const osc_robot_spec* spec) {
   }
 }
 
-// state == NULL: only build H (nv*nv) and f (nv).  Otherwise run one control step:
-// state is the STATE-double record (all zeros + flag 0 => Init path), updated in place.
+// state == NULL: only build H (nv*nv) and f (nv).
+// state != NULL, x == NULL: osc_setup -- fill the STATE-double record for this data.
+// otherwise: one control step; state is updated in place; x / y must hold the previous
+// step's solution on entry (read on the sparsity-change path) and receive the new one.
 extern "C" int osc_core_host_step(const osc_robot_spec* spec, const osc_settings* settings,
                                   const double* M, const double* C, const double* J,
                                   const double* bias, const double* targets, const double* mask,

@@ -261,3 +261,34 @@ def test_build_kernel_objective_matches_oracle(oracle, preset, config):
         sc = np.abs(Ho[:spec.nv, :spec.nv]).max()
         np.testing.assert_allclose(H[e], Ho[:spec.nv, :spec.nv], rtol=1e-12, atol=1e-12 * sc)
         np.testing.assert_allclose(f[e], fo[:spec.nv], rtol=1e-11, atol=1e-12 * np.abs(fo).max())
+
+
+def test_sparsity_change_reinit_path_on_device(oracle):
+    """update_optimization's fallback (:571-584): when the sparsity pattern of H/A changes,
+    the reference re-Inits OSQP and warm starts it from the previous solution.  The kernels
+    detect the change from a per-environment pattern signature kept in the state record."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("unitree_go2")
+    n_envs = 256
+    s0 = ob.synth.make_inputs(spec, n_envs, "go2_standing", step=0)
+    s1 = {k: v.copy() for k, v in ob.synth.make_inputs(spec, n_envs, "go2_standing", step=1).items()}
+    s1["M"][::2, 0, 1] = s1["M"][::2, 1, 0] = 1e-3   # every other environment changes pattern
+    s2 = ob.synth.make_inputs(spec, n_envs, "go2_standing", step=2)
+    b = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    b.setup(s0)
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(s0)
+    expected = 0
+    for t, inp in enumerate((s0, s1, s2)):
+        o = b.step(inp)
+        expected += o["reinits"]
+        g.step(inp)
+        r = g.results()
+        assert g.reinit_count() == expected, t
+        keep = o["margin"] > 1e-6
+        assert np.array_equal(r["iters"][keep], o["iters"][keep]), t
+        d = np.abs(r["torque"] - o["torque"])[keep]
+        tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
+        assert (d <= tol).all(), (t, (d / tol).max())
+    assert expected == n_envs  # n/2 at step 1 (zero -> non-zero) + n/2 at step 2 (back)

@@ -19,32 +19,28 @@ def run_host_core(L, spec, settings, steps, n_envs):
     from osc_b200 import capi
     cs = capi.c_spec(spec)
     SS = L.osc_core_host_state_size(C.byref(cs))
-    assert SS == spec.n + 2 * spec.m + spec.nv + 2
+    assert SS >= spec.n + 2 * spec.m + spec.nv + 2
     outs = [dict(torque=np.zeros((n_envs, spec.nu)), iters=np.zeros(n_envs, np.int32),
                  status=np.zeros(n_envs, np.int32), rho=np.zeros(n_envs),
+                 reinit=np.zeros(n_envs, np.int32),
                  x=np.zeros((n_envs, spec.n)), y=np.zeros((n_envs, spec.m))) for _ in steps]
-    ii = np.zeros(3, np.int32)
+    ii = np.zeros(4, np.int32)
     dd = np.zeros(3)
     for e in range(n_envs):
         state = np.zeros(SS)
-        H = np.zeros(spec.nv ** 2)
-        f = np.zeros(spec.nv)
         a = [np.ascontiguousarray(steps[0][k][e]) for k in FIELDS]
-        L.osc_core_host_step(C.byref(cs), C.byref(settings), *[_p(v) for v in a], None, None,
-                             None, None, None, None, _p(H), _p(f))
-        # osc_setup's state: cold iterates, previous linear cost = f, rho0, initialised
-        q0 = spec.n + 2 * spec.m
-        state[q0:q0 + spec.nv] = f
-        state[-2], state[-1] = settings.rho, 1.0
+        # osc_setup
+        L.osc_core_host_step(C.byref(cs), C.byref(settings), *[_p(v) for v in a], _p(state),
+                             None, None, None, None, None, None, None)
+        x = np.zeros(spec.n); y = np.zeros(spec.m); tq = np.zeros(spec.nu)
         for t, data in enumerate(steps):
             a = [np.ascontiguousarray(data[k][e]) for k in FIELDS]
-            x = np.zeros(spec.n); y = np.zeros(spec.m); tq = np.zeros(spec.nu)
             L.osc_core_host_step(C.byref(cs), C.byref(settings), *[_p(v) for v in a], _p(state),
                                  _p(x), _p(y), _p(tq), ii.ctypes.data_as(C.POINTER(C.c_int)),
                                  _p(dd), None, None)
             o = outs[t]
             o["torque"][e], o["x"][e], o["y"][e] = tq, x, y
-            o["iters"][e], o["status"][e], o["rho"][e] = ii[0], ii[1], dd[2]
+            o["iters"][e], o["status"][e], o["rho"][e], o["reinit"][e] = ii[0], ii[1], dd[2], ii[3]
     return outs
 
 
@@ -95,3 +91,29 @@ def test_objective_build_is_bitwise_close_to_oracle(oracle, host_core):
             assert np.all(fo[spec.nv:] == 0.0)
             np.testing.assert_array_equal(np.diag(Ho)[spec.nv:spec.nv + spec.nu],
                                           2 * (spec.w_reg + spec.w_torque))
+
+
+def test_sparsity_change_branch_matches_oracle(oracle, host_core):
+    """A structural zero of M becomes non-zero between steps: the reference re-Inits OSQP
+    (rho back to settings.rho, scaling with the current cost) and warm starts from the
+    previous unscaled solution (:571-584).  Same on the device code."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("unitree_go2")
+    N = 16
+    s0 = ob.synth.make_inputs(spec, N, "go2_standing", step=0)
+    s1 = {k: v.copy() for k, v in ob.synth.make_inputs(spec, N, "go2_standing", step=1).items()}
+    s1["M"][:, 0, 1] = s1["M"][:, 1, 0] = 1e-3
+    s2 = ob.synth.make_inputs(spec, N, "go2_standing", step=2)  # pattern changes back
+    steps = [s0, s1, s2]
+    b = oracle.OracleBatch(spec, N, oracle.default_settings())
+    b.setup(s0)
+    ref = [b.step(s) for s in steps]
+    assert [r["reinits"] for r in ref] == [0, N, N]
+    st = capi.CSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 5.0, 10, 1, 0, 4000, 25, 1)
+    got = run_host_core(host_core, spec, st, steps, N)
+    for t in range(3):
+        assert got[t]["reinit"].sum() == ref[t]["reinits"]
+        np.testing.assert_array_equal(got[t]["iters"], ref[t]["iters"])
+        d = np.abs(got[t]["torque"] - ref[t]["torque"])
+        assert (d <= ATOL + RTOL * np.abs(ref[t]["torque"])).all(), (t, d.max())
