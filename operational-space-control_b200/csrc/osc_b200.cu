@@ -260,15 +260,8 @@ __global__ void init_state_kernel(double* __restrict__ state, const double* __re
     const double* Mm = M + (size_t)env * NV * NV;
     const double* Jc = J + ((size_t)env * D::S + D::JC0) * NV;
     auto bit = [&](int b) -> bool {
-      if (b < D::NTRI) {
-        int i = 0, j = b;
-        while (j > i) {
-          j -= i + 1;
-          ++i;
-        }
-        return H[i * NV + j] != 0.0;
-      }
-      b -= D::NTRI;
+      if (b < NV * NV) return H[b] != 0.0;
+      b -= NV * NV;
       if (b < NV * NV) return Mm[b] != 0.0;
       b -= NV * NV;
       if (b < NV * D::NZ) return Jc[b] != 0.0;
