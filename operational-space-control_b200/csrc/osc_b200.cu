@@ -510,6 +510,8 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
 
 template <class D>
 int launch_solve(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  if (h->solve_warps_pref == 4) return launch_solve_w<D, 4>(h, st, env0, n, counter);
+  if (h->solve_warps_pref == 8) return launch_solve_w<D, 8>(h, st, env0, n, counter);
   if (h->solve_warps_pref == 12 || solve_warps_hi<D>() == solve_warps_lo<D>())
     return launch_solve_w<D, solve_warps_lo<D>()>(h, st, env0, n, counter);
   return launch_solve_w<D, solve_warps_hi<D>()>(h, st, env0, n, counter);
