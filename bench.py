@@ -310,6 +310,7 @@ def main():
     gather_ms = None
     if world > 1:
         tq_dev = torch.from_numpy(np.ascontiguousarray(tq)).to(dev)
+        sharding.all_gather_rows(tq_dev, world * n_envs, world)  # NCCL lazy init, untimed
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
@@ -348,6 +349,8 @@ def main():
                 "peak_source": "DFMA micro-benchmark run inside this bench "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_solve": flops / n_envs, "iters_mean": k_mean,
+                "ncu_busiest_unit": "LSU data pipe (shared-memory wavefronts) 70 % of peak; "
+                                    "FP64 pipe 24 %, issue slots 41 % (profiles/r1d_ncu_summary.md)",
                 "launch_ms": kt.solve_ms,
                 "hbm_view": {"achieved_gbs": spec.algorithmic_bytes * n_envs / (kt.solve_ms * 1e-3) / 1e9,
                              "peak_gbs": hbm_peak}}

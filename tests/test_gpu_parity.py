@@ -343,3 +343,37 @@ def test_two_handles_and_device_resident_inputs(oracle):
         gc.step(a_in)  # host path refuses while inputs are bound to caller memory
     gc.bind_device_inputs()
     np.testing.assert_allclose(gc.step(a_in), ga.step(a_in), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("preset,config,n_envs", [
+    ("unitree_go2", "go2_standing", 4096),                        # BASELINE configs[1]
+    ("walter_sr_true_tumbling_mjjoint", "tumbling", 16384),       # configs[2]
+    ("walter_sr_wheels", "stairs", 8192),                         # configs[3]
+])
+def test_parity_at_baseline_sizes(oracle, preset, config, n_envs):
+    """Full BASELINE.json batch sizes: cold step + warm step against the oracle (all host
+    cores), same gates as the small cases; prints the statistics quoted in profiles/."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    steps = [ob.synth.make_inputs(spec, n_envs, config, step=t) for t in range(2)]
+    ref = _oracle_steps(oracle, spec, n_envs, steps)
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(steps[0])
+    for t, inp in enumerate(steps):
+        g.step(inp)
+        r = g.results()
+        o = ref[t]
+        keep = o["repro"]
+        same_it = (r["iters"] == o["iters"])
+        d = np.abs(r["torque"] - o["torque"])
+        tol = ATOL + RTOL * np.abs(o["torque"])
+        ratio = (d / tol).max(1)
+        print(f"PARITY {preset} {config} N={n_envs} step={t}: reproducible {keep.mean():.5f}, "
+              f"iters equal (all) {same_it.mean():.5f}, within tol (all) {(ratio <= 1).mean():.5f}, "
+              f"worst ratio (gated) {ratio[keep].max():.3g}, iters mean {o['iters'].mean():.1f}, "
+              f"solved {(r['status'] == capi.SOLVED).mean():.5f}")
+        assert keep.mean() > 0.99
+        assert same_it[keep].all()
+        assert np.array_equal(r["status"][keep], o["status"][keep])
+        assert (ratio[keep] <= 1).all()
