@@ -173,6 +173,38 @@ typedef struct {
 int osc_timing_enable(osc_handle *h, int on);
 int osc_timing_read(osc_handle *h, osc_kernel_times *out);
 
+/* ---- the step BEFORE the hot path: per-environment task-space PD
+ * targets and the contact mask, so a roll-out loop can keep both on the device. ---- */
+
+/* DEVICE pointers, [n_envs][ns][3] (pos, vel, angvel) / [n_envs][ns][4] (quat, w x y z).
+ * Desired velocities may be NULL (= 0); everything else is required. */
+typedef struct {
+  const double *pos, *quat, *vel, *angvel;
+  const double *pos_des, *quat_des, *vel_des, *angvel_des;
+} osc_site_state;
+
+/* examples/standing.cc:146-155 generalised to every task site (the Walter drivers' per-site
+ * laws are the same PD form, e.g. walter_sr_true_tumbling_mjjoint.cc:873-973):
+ *   targets[e][i][0:3] = kp_lin[i] (p_des - p) + kd_lin[i] (v_des - v)
+ *   targets[e][i][3:6] = kp_ang[i] vec(q_des (x) conj(q)) + kd_ang[i] (w_des - w)
+ * Gains are host arrays of ns entries.  Writes the handle's own `targets` input buffer. */
+int osc_targets_pd(osc_handle *h, const osc_site_state *s, const double *kp_lin,
+                   const double *kd_lin, const double *kp_ang, const double *kd_ang,
+                   void *stream);
+
+/* Contact mask from MuJoCo contact pairs (walter_sr_true_tumbling_mjjoint.cc:523-558):
+ * every contact k < ncon[e] whose geom[0] or geom[1] is a listed id (`wheel_sites_mujoco`,
+ * :436) contributes the first site on that geom's body (getSiteIdsOnSameBodyAsGeom, :106);
+ * mask[e][c] = 1.0 iff list[c] is among the contributed sites
+ * (getBinaryRepresentation_std_find, :152).
+ * geom_pairs: DEVICE int [n_envs][max_con][2]; ncon: DEVICE int [n_envs];
+ * contact_geom_ids: host int [nc] (the list); site_of_geom: host int [nc], the site each
+ * listed geom maps to, or NULL when site and geom ids coincide (the Walter models).
+ * Writes the handle's own `mask` input buffer. */
+int osc_contact_mask_from_contacts(osc_handle *h, const int *geom_pairs, const int *ncon,
+                                   int max_con, const int *contact_geom_ids,
+                                   const int *site_of_geom, void *stream);
+
 /* How many environment-steps so far took the reference's sparsity-change path
  * (update_optimization :571-584: UpdateObjectiveAndConstraintMatrices rejected the new
  * pattern -> solver re-Init with rho reset + SetWarmStart(solution, dual_solution)).

@@ -354,6 +354,72 @@ solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// The step before the hot path: task-space PD targets and contact masks (elementwise,
+// HBM-bound; one thread per (environment, site) / per environment)
+// ---------------------------------------------------------------------------
+struct PdGains {
+  double kp_lin[kMaxSites], kd_lin[kMaxSites], kp_ang[kMaxSites], kd_ang[kMaxSites];
+};
+
+__global__ void __launch_bounds__(256)
+targets_pd_kernel(const __grid_constant__ PdGains g, const double* __restrict__ pos,
+                  const double* __restrict__ quat, const double* __restrict__ vel,
+                  const double* __restrict__ angvel, const double* __restrict__ pos_des,
+                  const double* __restrict__ quat_des, const double* __restrict__ vel_des,
+                  const double* __restrict__ angvel_des, double* __restrict__ targets, int ns,
+                  long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int site = (int)(i % ns);
+    const double* p = pos + 3 * i;
+    const double* pd = pos_des + 3 * i;
+    const double* v = vel + 3 * i;
+    const double* w = angvel + 3 * i;
+    const double* q = quat + 4 * i;
+    const double* qd = quat_des + 4 * i;
+    // rotation error = vec(q_des (x) conj(q))   (standing.cc:151)
+    const double w1 = qd[0], x1 = qd[1], y1 = qd[2], z1 = qd[3];
+    const double w2 = q[0], x2 = -q[1], y2 = -q[2], z2 = -q[3];
+    const double ex = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+    const double ey = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+    const double ez = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+    const double e3[3] = {ex, ey, ez};
+    double* t = targets + 6 * i;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double vd = vel_des ? vel_des[3 * i + k] : 0.0;
+      const double wd = angvel_des ? angvel_des[3 * i + k] : 0.0;
+      t[k] = g.kp_lin[site] * (pd[k] - p[k]) + g.kd_lin[site] * (vd - v[k]);
+      t[3 + k] = g.kp_ang[site] * e3[k] + g.kd_ang[site] * (wd - w[k]);
+    }
+  }
+}
+
+struct ContactIds {
+  int id[kMaxNu];         // nc <= 16 listed geoms
+  unsigned bits[kMaxNu];  // mask entries a contact on listed geom j raises
+  int nc;
+};
+
+__global__ void __launch_bounds__(256)
+contact_mask_kernel(const __grid_constant__ ContactIds ids, const int* __restrict__ pairs,
+                    const int* __restrict__ ncon, int max_con, double* __restrict__ mask,
+                    int n_envs) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_envs; e += gridDim.x * blockDim.x) {
+    int n = ncon[e];
+    n = n < 0 ? 0 : (n > max_con ? max_con : n);
+    unsigned bits = 0;
+    const int2* pr = reinterpret_cast<const int2*>(pairs) + (size_t)e * max_con;
+    for (int k = 0; k < n; ++k) {
+      const int2 gp = pr[k];
+      for (int c = 0; c < ids.nc; ++c)
+        if (gp.x == ids.id[c] || gp.y == ids.id[c]) bits |= ids.bits[c];
+    }
+    for (int c = 0; c < ids.nc; ++c) mask[(size_t)e * ids.nc + c] = (bits >> c) & 1u ? 1.0 : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // FP64 FMA peak
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -872,6 +938,67 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
   }
   h->kernels_ready = true;
   OSC_CUDA(h, cudaStreamSynchronize(st));
+  return OSC_OK;
+}
+
+int osc_targets_pd(osc_handle* h, const osc_site_state* s, const double* kp_lin,
+                   const double* kd_lin, const double* kp_ang, const double* kd_ang,
+                   void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!s || !kp_lin || !kd_lin || !kp_ang || !kd_ang || !s->pos || !s->quat || !s->vel ||
+      !s->angvel || !s->pos_des || !s->quat_des) {
+    h->err = "osc_targets_pd: null argument";
+    return OSC_ERR_INVALID;
+  }
+  if (h->iTargets != h->dTargets) {
+    h->err = "osc_targets_pd: the targets input is bound to caller-owned memory";
+    return OSC_ERR_STATE;
+  }
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  osc::PdGains g{};
+  for (int i = 0; i < h->ns; ++i) {
+    g.kp_lin[i] = kp_lin[i]; g.kd_lin[i] = kd_lin[i];
+    g.kp_ang[i] = kp_ang[i]; g.kd_ang[i] = kd_ang[i];
+  }
+  const long long total = (long long)h->n_envs * h->ns;
+  int grid = (int)((total + 255) / 256);
+  if (grid > h->sm_count * 16) grid = h->sm_count * 16;
+  osc::targets_pd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      g, s->pos, s->quat, s->vel, s->angvel, s->pos_des, s->quat_des, s->vel_des, s->angvel_des,
+      h->dTargets, h->ns, total);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
+int osc_contact_mask_from_contacts(osc_handle* h, const int* geom_pairs, const int* ncon,
+                                   int max_con, const int* contact_geom_ids,
+                                   const int* site_of_geom, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!geom_pairs || !ncon || !contact_geom_ids || max_con < 0) {
+    h->err = "osc_contact_mask_from_contacts: bad argument";
+    return OSC_ERR_INVALID;
+  }
+  if (h->iMask != h->dMask) {
+    h->err = "osc_contact_mask_from_contacts: the mask input is bound to caller-owned memory";
+    return OSC_ERR_STATE;
+  }
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  osc::ContactIds ids{};
+  ids.nc = h->nc;
+  for (int j = 0; j < h->nc; ++j) {
+    ids.id[j] = contact_geom_ids[j];
+    // getBinaryRepresentation_std_find(sites hit, list): entry c is raised when the site of
+    // a touched listed geom equals list[c]
+    const int site = site_of_geom ? site_of_geom[j] : contact_geom_ids[j];
+    for (int c = 0; c < h->nc; ++c)
+      if (contact_geom_ids[c] == site) ids.bits[j] |= 1u << c;
+  }
+  int grid = (h->n_envs + 255) / 256;
+  osc::contact_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ids, geom_pairs, ncon, max_con,
+                                                                  h->dMask, h->n_envs);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
   return OSC_OK;
 }
 

@@ -27,6 +27,7 @@ EXPORTS = (
     "osc_download", "osc_sync", "osc_step_host", "osc_kernel_launches",
     "osc_measure_dfma_tflops", "osc_host_alloc", "osc_host_free", "osc_bind_device_inputs",
     "osc_timing_enable", "osc_timing_read", "osc_download_objective", "osc_reinit_count",
+    "osc_targets_pd", "osc_contact_mask_from_contacts",
 )
 
 
@@ -54,6 +55,11 @@ class CDeviceBuffers(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in (
         "M", "C", "J", "bias", "targets", "mask", "torque", "solution", "dual", "iters", "status",
         "pri_res", "dua_res", "rho")]
+
+
+class CSiteState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "pos", "quat", "vel", "angvel", "pos_des", "quat_des", "vel_des", "angvel_des")]
 
 
 class CKernelTimes(C.Structure):
@@ -99,6 +105,8 @@ def load():
     L.osc_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.osc_host_free.argtypes = [vp]
     L.osc_bind_device_inputs.argtypes = [vp] + [vp] * 6
+    L.osc_targets_pd.argtypes = [vp, C.POINTER(CSiteState), dp, dp, dp, dp, vp]
+    L.osc_contact_mask_from_contacts.argtypes = [vp, vp, vp, C.c_int, ip, ip, vp]
     L.osc_timing_enable.argtypes = [vp, C.c_int]
     L.osc_timing_read.argtypes = [vp, C.POINTER(CKernelTimes)]
     _LIB = L
@@ -274,6 +282,37 @@ class BatchedOSC:
         """Device pointers (ints) of caller-owned HBM buffers to read inputs from."""
         self._check(self.L.osc_bind_device_inputs(self.h, M, C_, J, bias, targets, mask),
                     "osc_bind_device_inputs")
+
+    def targets_pd(self, site_state: dict, kp_lin, kd_lin, kp_ang, kd_ang, stream=None):
+        """Task-space PD targets of every (environment, site) computed on the device into the
+        handle's `targets` input (examples/standing.cc:146-155).  site_state maps
+        pos/quat/vel/angvel/pos_des/quat_des[/vel_des/angvel_des] to DEVICE pointers (ints)."""
+        st = CSiteState(**{k: site_state.get(k) for k, _ in CSiteState._fields_})
+        g = [np.ascontiguousarray(a, dtype=np.float64) for a in (kp_lin, kd_lin, kp_ang, kd_ang)]
+        for a in g:
+            if a.shape != (self.spec.ns,):
+                raise ValueError(f"gains: expected shape ({self.spec.ns},), got {a.shape}")
+        dp = C.POINTER(C.c_double)
+        self._check(self.L.osc_targets_pd(self.h, C.byref(st), *[a.ctypes.data_as(dp) for a in g],
+                                          stream), "osc_targets_pd")
+
+    def contact_mask_from_contacts(self, geom_pairs_dev: int, ncon_dev: int, max_con: int,
+                                   contact_geom_ids, site_of_geom=None, stream=None):
+        """Contact mask from MuJoCo contact geom pairs resident on the device
+        (examples/walter_sr_true_tumbling_mjjoint.cc:523-558) into the handle's `mask` input."""
+        ip = C.POINTER(C.c_int)
+        ids = np.ascontiguousarray(contact_geom_ids, dtype=np.int32)
+        if ids.shape != (self.spec.nc,):
+            raise ValueError(f"contact_geom_ids: expected shape ({self.spec.nc},)")
+        sog = None
+        if site_of_geom is not None:
+            sog = np.ascontiguousarray(site_of_geom, dtype=np.int32)
+            if sog.shape != ids.shape:
+                raise ValueError("site_of_geom: same shape as contact_geom_ids")
+        self._check(self.L.osc_contact_mask_from_contacts(
+            self.h, geom_pairs_dev, ncon_dev, int(max_con), ids.ctypes.data_as(ip),
+            sog.ctypes.data_as(ip) if sog is not None else None, stream),
+            "osc_contact_mask_from_contacts")
 
     def enable_timing(self, on: bool = True):
         self._check(self.L.osc_timing_enable(self.h, int(on)), "osc_timing_enable")

@@ -377,3 +377,81 @@ def test_parity_at_baseline_sizes(oracle, preset, config, n_envs):
         assert same_it[keep].all()
         assert np.array_equal(r["status"][keep], o["status"][keep])
         assert (ratio[keep] <= 1).all()
+
+
+def test_targets_pd_and_contact_mask_kernels_match_oracle(oracle):
+    """the step before the hot path on the device.  FP64 elementwise:
+    the PD targets must equal the numpy restatement to 1 ulp-level (products are not fused
+    identically, so 1e-12 relative), the contact mask bit-exactly; the control step that
+    consumes them must equal the step on host-uploaded targets/mask bit-exactly."""
+    import torch
+    import osc_b200 as ob
+    import osc_targets as ot
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr_true_tumbling_mjjoint")
+    n_envs, ns, nc = 777, spec.ns, spec.nc
+    rng = np.random.default_rng(5)
+    st = {k: rng.standard_normal((n_envs, ns, 3)) for k in
+          ("pos", "vel", "angvel", "pos_des", "vel_des", "angvel_des")}
+    for k in ("quat", "quat_des"):
+        q = rng.standard_normal((n_envs, ns, 4))
+        st[k] = q / np.linalg.norm(q, axis=-1, keepdims=True)
+    gains = rng.uniform(1.0, 2400.0, (4, ns))
+    listed = np.array([3, 4, 7, 8, 11, 12, 15, 16], np.int32)
+    max_con = 12
+    pairs = rng.integers(0, 20, (n_envs, max_con, 2)).astype(np.int32)
+    ncon = rng.integers(0, max_con + 1, n_envs).astype(np.int32)
+    ncon[:3] = [0, max_con, 1]
+    site_of = np.array([3, 3, 7, 8, 11, 12, 16, 16], np.int32)
+
+    inp = ob.synth.make_inputs(spec, n_envs, "tumbling", step=0)
+    g = capi.BatchedOSC(spec, n_envs)
+    g.upload(inp)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in st.items()}
+    dpairs, dncon = torch.from_numpy(pairs).cuda(), torch.from_numpy(ncon).cuda()
+    torch.cuda.synchronize()
+    buf = g.device_buffers()
+
+    def read(ptr, shape):
+        out = torch.empty(shape, dtype=torch.float64, device="cuda")
+        import ctypes as C
+        C.CDLL("libcudart.so.12").cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(ptr),
+                                             C.c_size_t(out.numel() * 8), 3)
+        return out.cpu().numpy()
+
+    for with_des, sog in ((True, None), (False, site_of)):
+        ptrs = {k: v.data_ptr() for k, v in dev.items()}
+        if not with_des:
+            ptrs["vel_des"] = ptrs["angvel_des"] = None
+        g.targets_pd(ptrs, *gains)
+        g.contact_mask_from_contacts(dpairs.data_ptr(), dncon.data_ptr(), max_con, listed, sog)
+        g.sync()
+        t_ref = ot.targets_pd(st["pos"], st["quat"], st["vel"], st["angvel"], st["pos_des"],
+                              st["quat_des"], *gains,
+                              vel_des=st["vel_des"] if with_des else None,
+                              angvel_des=st["angvel_des"] if with_des else None)
+        m_ref = ot.contact_mask_from_contacts(pairs, ncon, listed, sog)
+        t_gpu = read(buf.targets, (n_envs, ns, 6))
+        m_gpu = read(buf.mask, (n_envs, nc))
+        np.testing.assert_allclose(t_gpu, t_ref, rtol=1e-12, atol=1e-9)
+        assert np.array_equal(m_gpu, m_ref)
+        assert 0.05 < m_ref.mean() < 0.95
+    # the control step on device-made targets/mask == the step on the same values uploaded
+    g.setup()
+    g.step_device()
+    a = g.results()
+    g2 = capi.BatchedOSC(spec, n_envs)
+    inp2 = dict(inp, targets=t_gpu, mask=m_gpu)
+    g2.setup(inp2)
+    g2.step_device()
+    b = g2.results()
+    assert np.array_equal(a["torque"], b["torque"]) and np.array_equal(a["iters"], b["iters"])
+    # and matches the oracle on those inputs
+    ref = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    ref.setup(inp2)
+    o = ref.step(inp2)
+    keep = o["margin"] > 1e-6
+    d = np.abs(a["torque"] - o["torque"])[keep]
+    tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
+    assert np.array_equal(a["iters"][keep], o["iters"][keep])
+    assert (d <= tol).mean() > 0.99
