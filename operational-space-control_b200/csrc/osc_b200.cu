@@ -353,6 +353,62 @@ solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
   }
 }
 
+// K3 for robots with 2 nv <= 32: osc::Core3 (register-resident iteration matrices, two lanes
+// per dynamics row).  Same loading scheme and arguments as solve_kernel.
+template <class D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
+  using WS = Workspace3<D>;
+  using C3 = Core3<D>;
+  constexpr int NV = D::NV;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WS* wsb = reinterpret_cast<WS*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WARPS * sizeof(WS));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WS& w = wsb[warp];
+  uint64_t* bar = &bars[warp];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  constexpr uint32_t kBytes =
+      sizeof(double) * (NV * NV + NV * NV + D::NZ * NV + D::STATE + NV + NV + D::NC);
+  for (;;) {
+    int env = 0;
+    if (lane == 0) env = atomicAdd(a.counter, 1);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= a.n_envs) break;
+    if (lane == 0) {
+      fence_proxy_async();  // order the previous environment's generic-proxy accesses
+      mbar_expect_tx(bar, kBytes);
+      bulk_g2s(w.Ae, a.M + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
+      bulk_g2s(w.Pdv, a.Hdv + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
+      bulk_g2s(w.scratch, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(double) * D::NZ * NV,
+               bar);
+      bulk_g2s(w.land, a.state + (size_t)env * D::STATE, sizeof(double) * D::STATE, bar);
+      bulk_g2s(w.Cv, a.C + (size_t)env * NV, sizeof(double) * NV, bar);
+      bulk_g2s(w.fv, a.fdv + (size_t)env * NV, sizeof(double) * NV, bar);
+      bulk_g2s(w.maskv, a.mask + (size_t)env * D::NC, sizeof(double) * D::NC, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const Result r = C3::step(w, p, lane, a.fdv + (size_t)env * NV, a.sol_x + (size_t)env * D::N,
+                              a.sol_y + (size_t)env * D::M, a.torque + (size_t)env * D::NU,
+                              a.state + (size_t)env * D::STATE);
+    if (lane == 0) {
+      a.iters[env] = r.iter;
+      a.status[env] = r.status;
+      a.pri_res[env] = r.pri_res;
+      a.dua_res[env] = r.dua_res;
+      a.rho[env] = r.rho;
+      if (r.reinit) atomicAdd(a.reinits, 1);
+    }
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // The step before the hot path: task-space PD targets and contact masks (elementwise,
 // HBM-bound; one thread per (environment, site) / per environment)
@@ -460,6 +516,7 @@ struct osc_handle {
   cudaEvent_t fence_ev;
   int n_counters;
   int solve_warps_pref;
+  int solve_core;       // 2: force the generic core (OSC_B200_SOLVE_CORE=2), else by robot shape
   int build_grid_max;   // resident CTAs of build_qp_kernel on the device
   bool kernels_ready;
   // optional per-kernel timing
@@ -574,8 +631,40 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   return OSC_OK;
 }
 
+constexpr int kSolve3Warps = 8;  // 255 registers per thread; Workspace3 x 8 fits easily
+
+template <class D>
+int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  constexpr int WARPS = kSolve3Warps;
+  const size_t smem = WARPS * sizeof(osc::Workspace3<D>) + WARPS * sizeof(uint64_t);
+  auto kern = osc::solve_kernel3<D, WARPS>;
+  if (!h->kernels_ready)
+    OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = h->sm_count;
+  const int need = (n + WARPS - 1) / WARPS;
+  if (grid > need) grid = need;
+  OSC_CUDA(h, cudaMemsetAsync(h->dCounter + counter, 0, sizeof(int), st));
+  const size_t e = (size_t)env0;
+  osc::SolveArgs a;
+  a.M = h->iM + e * D::NV * D::NV; a.C = h->iC + e * D::NV; a.J = h->iJ + e * D::S * D::NV;
+  a.mask = h->iMask + e * D::NC; a.Hdv = h->dH + e * D::NV * D::NV; a.fdv = h->dF + e * D::NV;
+  a.state = h->dState + e * D::STATE;
+  a.torque = h->dTorque + e * D::NU; a.sol_x = h->dX + e * D::N; a.sol_y = h->dY + e * D::M;
+  a.pri_res = h->dPri + e; a.dua_res = h->dDua + e; a.rho = h->dRho + e;
+  a.iters = h->dIters + e; a.status = h->dStatus + e; a.counter = h->dCounter + counter;
+  a.reinits = h->dCounter + h->n_counters;
+  a.n_envs = n;
+  kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
 template <class D>
 int launch_solve(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  if constexpr (osc::kUseCore3<D>) {
+    if (h->solve_core != 2) return launch_solve3<D>(h, st, env0, n, counter);
+  }
   if (h->solve_warps_pref == 4) return launch_solve_w<D, 4>(h, st, env0, n, counter);
   if (h->solve_warps_pref == 8) return launch_solve_w<D, 8>(h, st, env0, n, counter);
   if (h->solve_warps_pref == 12 || solve_warps_hi<D>() == solve_warps_lo<D>())
@@ -674,6 +763,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   {
     const char* e = getenv("OSC_B200_SOLVE_WARPS");
     h->solve_warps_pref = e ? atoi(e) : 12;  // measured equal at 16 (128 regs, spills)
+    const char* c = getenv("OSC_B200_SOLVE_CORE");
+    h->solve_core = c ? atoi(c) : 0;
   }
   if ((ce = cudaMalloc((void**)&h->dCounter, (h->n_counters + 1) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");

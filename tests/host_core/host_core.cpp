@@ -1,9 +1,11 @@
 // tests/host_core/host_core.cpp -- TEST HARNESS ONLY.
-// Instantiates the product's per-environment algorithm (csrc/osc_core.cuh) with
-// LANES = 1 on the host so that `pytest -m "not gpu"` can compare the exact code
-// the GPU runs against the oracle.  Never linked into libosc_b200.so.
+// Instantiates the product's per-environment algorithm on the host so that
+// `pytest -m "not gpu"` can compare the exact code the GPU runs against the oracle:
+// csrc/osc_core3.cuh with an emulated 32-lane warp (osc_warp.cuh) for the Walter robots,
+// csrc/osc_core.cuh with LANES = 1 for the Go2.  Never linked into libosc_b200.so.
 #include <cstring>
 #include <memory>
+#include <type_traits>
 
 #include "../../operational-space-control_b200/csrc/osc_params.h"
 
@@ -12,9 +14,10 @@ template <class D>
 int run(const osc::Params& p, const double* M, const double* C, const double* J,
         const double* bias, const double* targets, const double* mask, double* state, double* x,
         double* y, double* torque, int* info_i, double* info_d, double* Hdv_out, double* f_out) {
-  using Core = osc::Core<D, 1>;
+  using Core = std::conditional_t<osc::kUseCore3<D>, osc::Core3<D>, osc::Core<D, 1>>;
+  using WSpace = std::conditional_t<osc::kUseCore3<D>, osc::Workspace3<D>, osc::Workspace<D>>;
   using B = osc::BuildQP<D>;
-  auto ws = std::make_unique<osc::Workspace<D>>();
+  auto ws = std::make_unique<WSpace>();
   std::memset(ws.get(), 0, sizeof(*ws));
   // objective build (the build kernel's per-item functions)
   double H[D::NV * D::NV], f[D::NV];
