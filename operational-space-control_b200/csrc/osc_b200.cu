@@ -354,7 +354,10 @@ solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
 }
 
 // K3 for robots with 2 nv <= 32: osc::Core3 (register-resident iteration matrices, two lanes
-// per dynamics row).  Same loading scheme and arguments as solve_kernel.
+// per dynamics row).  One warp per environment, persistent CTAs, dynamic work counter.  Every
+// warp owns a landing stage for one environment's input record; as soon as step_prepare() has
+// consumed it the warp draws its next environment and lands it there with TMA bulk copies
+// while step_solve() factorises and iterates on the current one.
 template <class D, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
@@ -372,31 +375,43 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     fence_mbar_init();
   }
   __syncwarp();
-  uint32_t parity = 0;
-  constexpr uint32_t kBytes =
-      sizeof(double) * (NV * NV + NV * NV + D::NZ * NV + D::STATE + NV + NV + D::NC);
-  for (;;) {
+  constexpr uint32_t kBytes = sizeof(typename WS::Stage);
+  static_assert(sizeof(typename WS::Stage) ==
+                    sizeof(double) * (2 * NV * NV + D::NZ * NV + D::STATE + 2 * NV + D::NC),
+                "the landing stage is exactly the seven bulk copies");
+  // lane 0: draw the next environment and start landing it (returns the index to all lanes)
+  auto fetch = [&]() -> int {
     int env = 0;
-    if (lane == 0) env = atomicAdd(a.counter, 1);
-    env = __shfl_sync(0xffffffffu, env, 0);
-    if (env >= a.n_envs) break;
     if (lane == 0) {
-      fence_proxy_async();  // order the previous environment's generic-proxy accesses
-      mbar_expect_tx(bar, kBytes);
-      bulk_g2s(w.Ae, a.M + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
-      bulk_g2s(w.Pdv, a.Hdv + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
-      bulk_g2s(w.scratch, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(double) * D::NZ * NV,
-               bar);
-      bulk_g2s(w.land, a.state + (size_t)env * D::STATE, sizeof(double) * D::STATE, bar);
-      bulk_g2s(w.Cv, a.C + (size_t)env * NV, sizeof(double) * NV, bar);
-      bulk_g2s(w.fv, a.fdv + (size_t)env * NV, sizeof(double) * NV, bar);
-      bulk_g2s(w.maskv, a.mask + (size_t)env * D::NC, sizeof(double) * D::NC, bar);
+      env = atomicAdd(a.counter, 1);
+      if (env < a.n_envs) {
+        fence_proxy_async();  // the stage's generic-proxy reads are ordered before the copies
+        mbar_expect_tx(bar, kBytes);
+        bulk_g2s(w.in.M, a.M + (size_t)env * NV * NV, sizeof(w.in.M), bar);
+        bulk_g2s(w.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(w.in.H), bar);
+        bulk_g2s(w.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(w.in.Jc), bar);
+        bulk_g2s(w.in.land, a.state + (size_t)env * D::STATE, sizeof(w.in.land), bar);
+        bulk_g2s(w.in.Cv, a.C + (size_t)env * NV, sizeof(w.in.Cv), bar);
+        bulk_g2s(w.in.fv, a.fdv + (size_t)env * NV, sizeof(w.in.fv), bar);
+        bulk_g2s(w.in.maskv, a.mask + (size_t)env * D::NC, sizeof(w.in.maskv), bar);
+      }
     }
+    return __shfl_sync(0xffffffffu, env, 0);
+  };
+  uint32_t parity = 0;
+  int env = fetch();
+  while (env < a.n_envs) {
     mbar_wait(bar, parity);
     parity ^= 1;
-    const Result r = C3::step(w, p, lane, a.fdv + (size_t)env * NV, a.sol_x + (size_t)env * D::N,
-                              a.sol_y + (size_t)env * D::M, a.torque + (size_t)env * D::NU,
-                              a.state + (size_t)env * D::STATE);
+    typename C3::Regs L;
+    double* sx = a.sol_x + (size_t)env * D::N;
+    double* sy = a.sol_y + (size_t)env * D::M;
+    double* so = a.state + (size_t)env * D::STATE;
+    const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy, so);
+    __syncwarp();
+    const int next = fetch();
+    const Result r = C3::step_solve(w, p, L, lane, pr, a.fdv + (size_t)env * NV, sx, sy,
+                                    a.torque + (size_t)env * D::NU, so);
     if (lane == 0) {
       a.iters[env] = r.iter;
       a.status[env] = r.status;
@@ -406,6 +421,7 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
       if (r.reinit) atomicAdd(a.reinits, 1);
     }
     __syncwarp();
+    env = next;
   }
 }
 

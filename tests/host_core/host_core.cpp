@@ -32,9 +32,17 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
   if (Hdv_out) std::memcpy(Hdv_out, H, sizeof(H));
   if (f_out) std::memcpy(f_out, f, sizeof(f));
   if (!state) return 0;
-  std::memcpy(ws->Ae, M, sizeof(double) * D::NV * D::NV);
-  std::memcpy(ws->Pdv, H, sizeof(H));
-  std::memcpy(ws->scratch, J + D::JC0 * D::NV, sizeof(double) * D::NZ * D::NV);
+  double *dM, *dH, *dJc, *dLand, *dC, *dF, *dMask;
+  if constexpr (osc::kUseCore3<D>) {
+    dM = ws->in.M; dH = ws->in.H; dJc = ws->in.Jc; dLand = ws->in.land;
+    dC = ws->in.Cv; dF = ws->in.fv; dMask = ws->in.maskv;
+  } else {
+    dM = ws->Ae; dH = ws->Pdv; dJc = ws->scratch; dLand = ws->land;
+    dC = ws->Cv; dF = ws->fv; dMask = ws->maskv;
+  }
+  std::memcpy(dM, M, sizeof(double) * D::NV * D::NV);
+  std::memcpy(dH, H, sizeof(H));
+  std::memcpy(dJc, J + D::JC0 * D::NV, sizeof(double) * D::NZ * D::NV);
   if (!x) {
     // osc_setup (init_state_kernel): cold iterates, previous linear cost = f, rho0,
     // initialised flag, sparsity signature of the set-up data
@@ -45,10 +53,10 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
     for (int q = 0; q < D::SIG; ++q) state[D::SIG0 + q] = Core::as_f64(Core::sig_word(*ws, q, 0));
     return 0;
   }
-  std::memcpy(ws->land, state, sizeof(double) * D::STATE);
-  std::memcpy(ws->Cv, C, sizeof(double) * D::NV);
-  std::memcpy(ws->fv, f, sizeof(f));
-  std::memcpy(ws->maskv, mask, sizeof(double) * D::NC);
+  std::memcpy(dLand, state, sizeof(double) * D::STATE);
+  std::memcpy(dC, C, sizeof(double) * D::NV);
+  std::memcpy(dF, f, sizeof(f));
+  std::memcpy(dMask, mask, sizeof(double) * D::NC);
   osc::Result r = Core::step(*ws, p, 0, f, x, y, torque, state);
   info_i[0] = r.iter;
   info_i[1] = r.status;
