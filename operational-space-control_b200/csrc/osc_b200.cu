@@ -532,6 +532,7 @@ struct osc_handle {
   cudaEvent_t fence_ev;
   int n_counters;
   int solve_warps_pref;
+  int solve3_warps;
   int solve_core;       // 2: force the generic core (OSC_B200_SOLVE_CORE=2), else by robot shape
   int build_grid_max;   // resident CTAs of build_qp_kernel on the device
   bool kernels_ready;
@@ -649,9 +650,8 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
 
 constexpr int kSolve3Warps = 8;  // 255 registers per thread; Workspace3 x 8 fits easily
 
-template <class D>
-int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
-  constexpr int WARPS = kSolve3Warps;
+template <class D, int WARPS>
+int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
   const size_t smem = WARPS * sizeof(osc::Workspace3<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::solve_kernel3<D, WARPS>;
   if (!h->kernels_ready)
@@ -674,6 +674,13 @@ int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;
+}
+
+template <class D>
+int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  // OSC_B200_SOLVE3_WARPS=4: occupancy experiment (one warp per scheduler)
+  if (h->solve3_warps == 4) return launch_solve3w<D, 4>(h, st, env0, n, counter);
+  return launch_solve3w<D, kSolve3Warps>(h, st, env0, n, counter);
 }
 
 template <class D>
@@ -781,6 +788,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
     h->solve_warps_pref = e ? atoi(e) : 12;  // measured equal at 16 (128 regs, spills)
     const char* c = getenv("OSC_B200_SOLVE_CORE");
     h->solve_core = c ? atoi(c) : 0;
+    const char* w3 = getenv("OSC_B200_SOLVE3_WARPS");
+    h->solve3_warps = w3 ? atoi(w3) : kSolve3Warps;
   }
   if ((ce = cudaMalloc((void**)&h->dCounter, (h->n_counters + 1) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");

@@ -61,7 +61,33 @@ struct Warp {
     }
     return v;
   }
-  static OSC_HD unsigned ballot(const Var<bool>& p) { return __ballot_sync(kFull, p.v); }
+  // Warp-wide maxima of 16 non-negative quantities at once: a transposing butterfly (every
+  // level halves the number of quantities a lane carries: 8+4+2+1+1 = 16 shuffles instead of
+  // 16 x 5), after which lane l holds quantity (l >> 1) & 15; the results go through `scratch`
+  // (16 doubles of shared memory) to `out`, which every lane receives.
+  static OSC_HD void max16(Var<double> (&m)[16], double* out, double* scratch, int lane) {
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = m[q].v;
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {  // h = quantities kept; partner offset = 2 h
+      const bool up = (lane & (2 * h)) != 0;
+#pragma unroll
+      for (int q = 0; q < h; ++q) {
+        const double keep = up ? v[q + h] : v[q];
+        const double send = up ? v[q] : v[q + h];
+        const double t = __shfl_xor_sync(kFull, send, 2 * h);
+        v[q] = t > keep ? t : keep;
+      }
+    }
+    const double t = __shfl_xor_sync(kFull, v[0], 1);
+    v[0] = t > v[0] ? t : v[0];
+    __syncwarp();
+    if (!(lane & 1)) scratch[lane >> 1] = v[0];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) out[q] = scratch[q];
+  }
   // FP64 tensor-core tile product D(8x8) += A(8x4) B(4x8), PTX fragment layout of
   // mma.sync.m8n8k4.f64: lane = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
   static OSC_HD void mma884(Var<double>& d0, Var<double>& d1, const Var<double>& a,
@@ -113,6 +139,13 @@ struct Warp {
     for (int l = 0; l < 32; ++l)
       if (p.v[l]) b |= 1u << l;
     return b;
+  }
+  static void max16(Var<double> (&m)[16], double* out, double* scratch, int) {
+    for (int q = 0; q < 16; ++q) {
+      double v = m[q].v[0];
+      for (int l = 1; l < 32; ++l) v = m[q].v[l] > v ? m[q].v[l] : v;
+      out[q] = scratch[q] = v;
+    }
   }
   static void mma884(Var<double>& d0, Var<double>& d1, const Var<double>& a,
                      const Var<double>& b) {
