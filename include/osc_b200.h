@@ -163,12 +163,16 @@ int osc_bind_device_inputs(osc_handle *h, const double *M, const double *C, cons
 int osc_host_alloc(size_t bytes, void **out);
 int osc_host_free(void *p);
 
-/* Per-kernel device timing: when enabled, every osc_step brackets its two kernels
- * with CUDA events on the launch stream; osc_timing_read synchronises, returns the
- * average milliseconds per step of each kernel since the last read, and resets. */
+/* Per-kernel device timing: when enabled, every osc_step brackets its kernels with CUDA
+ * events on the launch stream; osc_timing_read synchronises, returns the average
+ * milliseconds per step of each kernel since the last read, and resets.
+ * build = objective build (H, f); scale = OSQP scale_data (Ruiz equilibration; 0 for robots
+ * on the generic solver core, which scales inside the solve kernel); solve = assembly,
+ * factorisation, ADMM, un-scaling. */
 typedef struct {
   float build_ms, solve_ms;
   int steps;
+  float scale_ms;
 } osc_kernel_times;
 int osc_timing_enable(osc_handle *h, int on);
 int osc_timing_read(osc_handle *h, osc_kernel_times *out);

@@ -294,6 +294,7 @@ struct SolveArgs {
   double* state;
   double *torque, *sol_x, *sol_y, *pri_res, *dua_res, *rho;
   int *iters, *status;
+  const double* scal;  // scaling records of scale_kernel3 (Core3 path only)
   int* counter;
   int* reinits;
   int n_envs;
@@ -353,6 +354,68 @@ solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
   }
 }
 
+// K3a for robots with 2 nv <= 32: OSQP's scale_data (10 Ruiz passes) + the update-path decision
+// of update_optimization (:565-584), osc::Core3::ruiz.  Its own kernel because it needs a
+// third of the registers of the solve (more warps per SM hide its dependent max / rsqrt
+// chains): one warp per environment, persistent CTAs, dynamic work counter, the next
+// environment's bulk copies in flight while the passes run on registers.
+struct ScaleArgs {
+  const double *M, *J, *Hdv, *fdv;
+  double* state;  // reads previous f / flag / signature, updates the signature in place
+  double* scal;   // out: D, E, c, path flag per environment
+  int* counter;
+  int n_envs;
+};
+
+template <class D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
+  using RWS = RuizWorkspace<D>;
+  using C3 = Core3<D>;
+  constexpr int NV = D::NV, TAIL0 = D::N + 2 * D::M;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  RWS* wsb = reinterpret_cast<RWS*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WARPS * sizeof(RWS));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RWS& rw = wsb[warp];
+  uint64_t* bar = &bars[warp];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  constexpr uint32_t kBytes = sizeof(typename RWS::Stage);
+  static_assert(sizeof(typename RWS::Stage) ==
+                    sizeof(double) * (2 * NV * NV + D::NZ * NV + RWS::TAIL + NV),
+                "the landing stage is exactly the five bulk copies");
+  auto fetch = [&]() -> int {
+    int env = 0;
+    if (lane == 0) {
+      env = atomicAdd(a.counter, 1);
+      if (env < a.n_envs) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, kBytes);
+        bulk_g2s(rw.in.M, a.M + (size_t)env * NV * NV, sizeof(rw.in.M), bar);
+        bulk_g2s(rw.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(rw.in.H), bar);
+        bulk_g2s(rw.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(rw.in.Jc), bar);
+        bulk_g2s(rw.in.tail, a.state + (size_t)env * D::STATE + TAIL0, sizeof(rw.in.tail), bar);
+        bulk_g2s(rw.in.fv, a.fdv + (size_t)env * NV, sizeof(rw.in.fv), bar);
+      }
+    }
+    return __shfl_sync(0xffffffffu, env, 0);
+  };
+  uint32_t parity = 0;
+  int env = fetch();
+  while (env < a.n_envs) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    int next = a.n_envs;
+    C3::ruiz(rw, p, lane, a.scal + (size_t)env * C3::SCAL,
+             a.state + (size_t)env * D::STATE + D::SIG0, [&]() { next = fetch(); });
+    env = next;
+  }
+}
+
 // K3 for robots with 2 nv <= 32: osc::Core3 (register-resident iteration matrices, two lanes
 // per dynamics row).  One warp per environment, persistent CTAs, dynamic work counter.  Every
 // warp owns a landing stage for one environment's input record; as soon as step_prepare() has
@@ -377,8 +440,9 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   __syncwarp();
   constexpr uint32_t kBytes = sizeof(typename WS::Stage);
   static_assert(sizeof(typename WS::Stage) ==
-                    sizeof(double) * (2 * NV * NV + D::NZ * NV + D::STATE + 2 * NV + D::NC),
-                "the landing stage is exactly the seven bulk copies");
+                    sizeof(double) * (2 * NV * NV + D::NZ * NV + D::STATE + 2 * NV + D::NC +
+                                      C3::SCAL),
+                "the landing stage is exactly the eight bulk copies");
   // lane 0: draw the next environment and start landing it (returns the index to all lanes)
   auto fetch = [&]() -> int {
     int env = 0;
@@ -394,6 +458,7 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
         bulk_g2s(w.in.Cv, a.C + (size_t)env * NV, sizeof(w.in.Cv), bar);
         bulk_g2s(w.in.fv, a.fdv + (size_t)env * NV, sizeof(w.in.fv), bar);
         bulk_g2s(w.in.maskv, a.mask + (size_t)env * D::NC, sizeof(w.in.maskv), bar);
+        bulk_g2s(w.in.scal, a.scal + (size_t)env * C3::SCAL, sizeof(w.in.scal), bar);
       }
     }
     return __shfl_sync(0xffffffffu, env, 0);
@@ -407,7 +472,7 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     double* sx = a.sol_x + (size_t)env * D::N;
     double* sy = a.sol_y + (size_t)env * D::M;
     double* so = a.state + (size_t)env * D::STATE;
-    const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy, so);
+    const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy);
     __syncwarp();
     const int next = fetch();
     const Result r = C3::step_solve(w, p, L, lane, pr, a.fdv + (size_t)env * NV, sx, sy,
@@ -521,7 +586,7 @@ struct osc_handle {
   int nv, nu, nc, ns, n, m, s, state;
   // device buffers
   double *dM, *dC, *dJ, *dBias, *dTargets, *dMask;
-  double *dH, *dF, *dState;
+  double *dH, *dF, *dState, *dScal;
   double *dTorque, *dX, *dY, *dPri, *dDua, *dRho;
   int *dIters, *dStatus, *dCounter;
   // inputs actually read by the kernels (own buffers unless osc_bind_device_inputs)
@@ -533,6 +598,7 @@ struct osc_handle {
   int n_counters;
   int solve_warps_pref;
   int solve3_warps;
+  cudaEvent_t timing_mid;  // set while a timed step is being recorded: scale | solve boundary
   int solve_core;       // 2: force the generic core (OSC_B200_SOLVE_CORE=2), else by robot shape
   int build_grid_max;   // resident CTAs of build_qp_kernel on the device
   bool kernels_ready;
@@ -650,6 +716,34 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
 
 constexpr int kSolve3Warps = 8;  // 255 registers per thread; Workspace3 x 8 fits easily
 
+constexpr int kScale3Warps = 12;  // <= 168 registers per thread
+
+template <class D>
+int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  constexpr int WARPS = kScale3Warps;
+  const size_t smem = WARPS * sizeof(osc::RuizWorkspace<D>) + WARPS * sizeof(uint64_t);
+  auto kern = osc::scale_kernel3<D, WARPS>;
+  if (!h->kernels_ready)
+    OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = h->sm_count;
+  const int need = (n + WARPS - 1) / WARPS;
+  if (grid > need) grid = need;
+  int* ctr = h->dCounter + h->n_counters + 1 + counter;  // second bank of work counters
+  OSC_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(int), st));
+  const size_t e = (size_t)env0;
+  osc::ScaleArgs a;
+  a.M = h->iM + e * D::NV * D::NV; a.J = h->iJ + e * D::S * D::NV;
+  a.Hdv = h->dH + e * D::NV * D::NV; a.fdv = h->dF + e * D::NV;
+  a.state = h->dState + e * D::STATE;
+  a.scal = h->dScal + e * osc::Core3<D>::SCAL;
+  a.counter = ctr;
+  a.n_envs = n;
+  kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
 template <class D, int WARPS>
 int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
   const size_t smem = WARPS * sizeof(osc::Workspace3<D>) + WARPS * sizeof(uint64_t);
@@ -669,6 +763,7 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   a.pri_res = h->dPri + e; a.dua_res = h->dDua + e; a.rho = h->dRho + e;
   a.iters = h->dIters + e; a.status = h->dStatus + e; a.counter = h->dCounter + counter;
   a.reinits = h->dCounter + h->n_counters;
+  a.scal = h->dScal + e * osc::Core3<D>::SCAL;
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
@@ -678,6 +773,9 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
 
 template <class D>
 int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  int rc = launch_scale3<D>(h, st, env0, n, counter);
+  if (rc) return rc;
+  if (h->timing_mid) OSC_CUDA(h, cudaEventRecord(h->timing_mid, st));
   // OSC_B200_SOLVE3_WARPS=4: occupancy experiment (one warp per scheduler)
   if (h->solve3_warps == 4) return launch_solve3w<D, 4>(h, st, env0, n, counter);
   return launch_solve3w<D, kSolve3Warps>(h, st, env0, n, counter);
@@ -775,7 +873,7 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
       {&h->dBias, N * h->s}, {&h->dTargets, N * h->s}, {&h->dMask, N * h->nc},
       {&h->dH, N * h->nv * h->nv}, {&h->dF, N * h->nv}, {&h->dState, N * h->state},
       {&h->dTorque, N * h->nu}, {&h->dX, N * h->n}, {&h->dY, N * h->m},
-      {&h->dPri, N}, {&h->dDua, N}, {&h->dRho, N}};
+      {&h->dPri, N}, {&h->dDua, N}, {&h->dRho, N}, {&h->dScal, N * (size_t)(h->n + h->m + 2)}};
   for (auto& b : bufs) {
     if ((ce = cudaMalloc((void**)b.p, b.n * sizeof(double))) != cudaSuccess) return fail(ce, "cudaMalloc");
     if ((ce = cudaMemset(*b.p, 0, b.n * sizeof(double))) != cudaSuccess) return fail(ce, "cudaMemset");
@@ -791,15 +889,18 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
     const char* w3 = getenv("OSC_B200_SOLVE3_WARPS");
     h->solve3_warps = w3 ? atoi(w3) : kSolve3Warps;
   }
-  if ((ce = cudaMalloc((void**)&h->dCounter, (h->n_counters + 1) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  // work counters of the solve launches [0, n), the re-Init count [n], work counters of the
+  // scale launches [n + 1, 2n + 1)
+  if ((ce = cudaMalloc((void**)&h->dCounter, (2 * h->n_counters + 1) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");
   if ((ce = cudaEventCreateWithFlags(&h->fence_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
-  cudaMemset(h->dCounter, 0, (h->n_counters + 1) * sizeof(int));
+  cudaMemset(h->dCounter, 0, (2 * h->n_counters + 1) * sizeof(int));
   cudaMemset(h->dIters, 0, N * sizeof(int));
   cudaMemset(h->dStatus, 0, N * sizeof(int));
   h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
   h->iMask = h->dMask;
   h->timing = false;
+  h->timing_mid = nullptr;
   h->ev_used = 0;
   h->kernels_ready = false;
   h->build_grid_max = h->sm_count;
@@ -811,7 +912,7 @@ int osc_destroy(osc_handle* h) {
   if (!h) return OSC_ERR_INVALID;
   cudaSetDevice(h->device);
   double* d[] = {h->dM, h->dC, h->dJ, h->dBias, h->dTargets, h->dMask, h->dH, h->dF, h->dState,
-                 h->dTorque, h->dX, h->dY, h->dPri, h->dDua, h->dRho};
+                 h->dTorque, h->dX, h->dY, h->dPri, h->dDua, h->dRho, h->dScal};
   for (double* p : d) if (p) cudaFree(p);
   if (h->dIters) cudaFree(h->dIters);
   if (h->dStatus) cudaFree(h->dStatus);
@@ -873,24 +974,30 @@ int osc_step(osc_handle* h, void* stream) {
   OSC_CUDA(h, cudaSetDevice(h->device));
   cudaEvent_t* ev = nullptr;
   if (h->timing) {
-    if (h->ev_used + 3 > h->ev.size()) {
-      for (int i = 0; i < 3; ++i) {
+    if (h->ev_used + 4 > h->ev.size()) {
+      for (int i = 0; i < 4; ++i) {
         cudaEvent_t e;
         OSC_CUDA(h, cudaEventCreate(&e));
         h->ev.push_back(e);
       }
     }
     ev = &h->ev[h->ev_used];
-    h->ev_used += 3;
+    h->ev_used += 4;
     OSC_CUDA(h, cudaEventRecord(ev[0], st));
   }
   int rc = OSC_DISPATCH(h, launch_build, h, st, 0, h->n_envs);
   if (rc) return rc;
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
+  // ev[2] = scale | solve boundary: recorded by launch_solve3 between its two kernels; the
+  // generic core has no separate scale kernel (recorded here: scale_ms = 0)
+  const bool split = h->shape == osc::Shape::kWalter && h->solve_core != 2;
+  h->timing_mid = (ev && split) ? ev[2] : nullptr;
+  if (ev && !split) OSC_CUDA(h, cudaEventRecord(ev[2], st));
   rc = OSC_DISPATCH(h, launch_solve, h, st, 0, h->n_envs, 0);
+  h->timing_mid = nullptr;
   if (rc) return rc;
   h->kernels_ready = true;  // function attributes / occupancy are set from here on
-  if (ev) OSC_CUDA(h, cudaEventRecord(ev[2], st));
+  if (ev) OSC_CUDA(h, cudaEventRecord(ev[3], st));
   return OSC_OK;
 }
 
@@ -936,18 +1043,21 @@ int osc_timing_enable(osc_handle* h, int on) {
 int osc_timing_read(osc_handle* h, osc_kernel_times* out) {
   if (check_handle(h) || !out) return OSC_ERR_INVALID;
   OSC_CUDA(h, cudaSetDevice(h->device));
-  double b = 0.0, s = 0.0;
-  const int steps = (int)(h->ev_used / 3);
+  const int steps = (int)(h->ev_used / 4);
+  double b = 0, sc = 0, s = 0;
   for (int i = 0; i < steps; ++i) {
-    OSC_CUDA(h, cudaEventSynchronize(h->ev[3 * i + 2]));
-    float t0 = 0, t1 = 0;
-    OSC_CUDA(h, cudaEventElapsedTime(&t0, h->ev[3 * i], h->ev[3 * i + 1]));
-    OSC_CUDA(h, cudaEventElapsedTime(&t1, h->ev[3 * i + 1], h->ev[3 * i + 2]));
+    OSC_CUDA(h, cudaEventSynchronize(h->ev[4 * i + 3]));
+    float t0 = 0, t1 = 0, t2 = 0;
+    OSC_CUDA(h, cudaEventElapsedTime(&t0, h->ev[4 * i], h->ev[4 * i + 1]));
+    OSC_CUDA(h, cudaEventElapsedTime(&t1, h->ev[4 * i + 1], h->ev[4 * i + 2]));
+    OSC_CUDA(h, cudaEventElapsedTime(&t2, h->ev[4 * i + 2], h->ev[4 * i + 3]));
     b += t0;
-    s += t1;
+    sc += t1;
+    s += t2;
   }
   out->steps = steps;
   out->build_ms = steps ? (float)(b / steps) : 0.f;
+  out->scale_ms = steps ? (float)(sc / steps) : 0.f;
   out->solve_ms = steps ? (float)(s / steps) : 0.f;
   h->ev_used = 0;
   return OSC_OK;

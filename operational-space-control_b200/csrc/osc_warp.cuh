@@ -61,6 +61,7 @@ struct Warp {
     }
     return v;
   }
+  static OSC_HD unsigned ballot(const Var<bool>& p) { return __ballot_sync(kFull, p.v); }
   // Warp-wide maxima of 16 non-negative quantities at once: a transposing butterfly (every
   // level halves the number of quantities a lane carries: 8+4+2+1+1 = 16 shuffles instead of
   // 16 x 5), after which lane l holds quantity (l >> 1) & 15; the results go through `scratch`

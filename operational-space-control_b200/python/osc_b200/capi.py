@@ -63,7 +63,8 @@ class CSiteState(C.Structure):
 
 
 class CKernelTimes(C.Structure):
-    _fields_ = [("build_ms", C.c_float), ("solve_ms", C.c_float), ("steps", C.c_int)]
+    _fields_ = [("build_ms", C.c_float), ("solve_ms", C.c_float), ("steps", C.c_int),
+                ("scale_ms", C.c_float)]
 
 
 class OscError(RuntimeError):

@@ -50,13 +50,31 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
     std::memcpy(state + D::N + 2 * D::M, f, sizeof(f));
     state[D::N + 2 * D::M + D::NV] = p.rho0;
     state[D::N + 2 * D::M + D::NV + 1] = 1.0;
-    for (int q = 0; q < D::SIG; ++q) state[D::SIG0 + q] = Core::as_f64(Core::sig_word(*ws, q, 0));
+    for (int q = 0; q < D::SIG; ++q) {
+      if constexpr (osc::kUseCore3<D>)
+        state[D::SIG0 + q] = Core::as_f64(Core::sig_word(dH, dM, dJc, q, 0));
+      else
+        state[D::SIG0 + q] = Core::as_f64(Core::sig_word(*ws, q, 0));
+    }
     return 0;
   }
   std::memcpy(dLand, state, sizeof(double) * D::STATE);
   std::memcpy(dC, C, sizeof(double) * D::NV);
   std::memcpy(dF, f, sizeof(f));
   std::memcpy(dMask, mask, sizeof(double) * D::NC);
+  if constexpr (osc::kUseCore3<D>) {
+    // the equilibration kernel's part (scale_kernel3): Ruiz passes + path decision
+    auto rw = std::make_unique<osc::RuizWorkspace<D>>();
+    std::memset(rw.get(), 0, sizeof(*rw));
+    std::memcpy(rw->in.M, M, sizeof(rw->in.M));
+    std::memcpy(rw->in.H, H, sizeof(rw->in.H));
+    std::memcpy(rw->in.Jc, J + D::JC0 * D::NV, sizeof(rw->in.Jc));
+    std::memcpy(rw->in.tail, state + D::N + 2 * D::M, sizeof(rw->in.tail));
+    std::memcpy(rw->in.fv, f, sizeof(rw->in.fv));
+    Core::ruiz(*rw, p, 0, ws->in.scal, state + D::SIG0, [] {});
+    // (the solve kernel lands the state record after the equilibration kernel ran)
+    std::memcpy(dLand, state, sizeof(double) * D::STATE);
+  }
   osc::Result r = Core::step(*ws, p, 0, f, x, y, torque, state);
   info_i[0] = r.iter;
   info_i[1] = r.status;

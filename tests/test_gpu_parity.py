@@ -263,18 +263,21 @@ def test_build_kernel_objective_matches_oracle(oracle, preset, config):
         np.testing.assert_allclose(f[e], fo[:spec.nv], rtol=1e-11, atol=1e-12 * np.abs(fo).max())
 
 
-def test_sparsity_change_reinit_path_on_device(oracle):
+@pytest.mark.parametrize("preset,config", [("unitree_go2", "go2_standing"),
+                                           ("walter_sr_true_tumbling_mjjoint", "tumbling")])
+def test_sparsity_change_reinit_path_on_device(oracle, preset, config):
     """update_optimization's fallback (:571-584): when the sparsity pattern of H/A changes,
     the reference re-Inits OSQP and warm starts it from the previous solution.  The kernels
     detect the change from a per-environment pattern signature kept in the state record."""
     import osc_b200 as ob
     from osc_b200 import capi
-    spec = ob.load_preset("unitree_go2")
+    spec = ob.load_preset(preset)
     n_envs = 256
-    s0 = ob.synth.make_inputs(spec, n_envs, "go2_standing", step=0)
-    s1 = {k: v.copy() for k, v in ob.synth.make_inputs(spec, n_envs, "go2_standing", step=1).items()}
+    s0 = ob.synth.make_inputs(spec, n_envs, config, step=0)
+    s1 = {k: v.copy() for k, v in ob.synth.make_inputs(spec, n_envs, config, step=1).items()}
+    assert (s1["M"][:, 0, 1] == 0).all()
     s1["M"][::2, 0, 1] = s1["M"][::2, 1, 0] = 1e-3   # every other environment changes pattern
-    s2 = ob.synth.make_inputs(spec, n_envs, "go2_standing", step=2)
+    s2 = ob.synth.make_inputs(spec, n_envs, config, step=2)
     b = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
     b.setup(s0)
     g = capi.BatchedOSC(spec, n_envs)

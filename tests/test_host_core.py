@@ -93,18 +93,21 @@ def test_objective_build_is_bitwise_close_to_oracle(oracle, host_core):
                                           2 * (spec.w_reg + spec.w_torque))
 
 
-def test_sparsity_change_branch_matches_oracle(oracle, host_core):
+@pytest.mark.parametrize("preset,config", [("unitree_go2", "go2_standing"),
+                                           ("walter_sr_true_tumbling_mjjoint", "tumbling")])
+def test_sparsity_change_branch_matches_oracle(oracle, host_core, preset, config):
     """A structural zero of M becomes non-zero between steps: the reference re-Inits OSQP
     (rho back to settings.rho, scaling with the current cost) and warm starts from the
     previous unscaled solution (:571-584).  Same on the device code."""
     import osc_b200 as ob
     from osc_b200 import capi
-    spec = ob.load_preset("unitree_go2")
+    spec = ob.load_preset(preset)
     N = 16
-    s0 = ob.synth.make_inputs(spec, N, "go2_standing", step=0)
-    s1 = {k: v.copy() for k, v in ob.synth.make_inputs(spec, N, "go2_standing", step=1).items()}
+    s0 = ob.synth.make_inputs(spec, N, config, step=0)
+    s1 = {k: v.copy() for k, v in ob.synth.make_inputs(spec, N, config, step=1).items()}
+    assert (s1["M"][:, 0, 1] == 0).all()
     s1["M"][:, 0, 1] = s1["M"][:, 1, 0] = 1e-3
-    s2 = ob.synth.make_inputs(spec, N, "go2_standing", step=2)  # pattern changes back
+    s2 = ob.synth.make_inputs(spec, N, config, step=2)  # pattern changes back
     steps = [s0, s1, s2]
     b = oracle.OracleBatch(spec, N, oracle.default_settings())
     b.setup(s0)

@@ -24,13 +24,13 @@ def main():
         g.step_device(); g.sync()
         t = g.read_timing()
         r = g.results()
-        print(f"cold: build {t.build_ms:.3f} ms solve {t.solve_ms:.3f} ms -> {N/(t.build_ms+t.solve_ms)*1e3:.3e} solves/s; iters mean {r['iters'].mean():.1f} hist {np.bincount(r['iters']//25)}")
+        print(f"cold: build {t.build_ms:.3f} ms scale {t.scale_ms:.3f} ms solve {t.solve_ms:.3f} ms -> {N/(t.build_ms+t.scale_ms+t.solve_ms)*1e3:.3e} solves/s; iters mean {r['iters'].mean():.1f} hist {np.bincount(r['iters']//25)}")
     for rep in range(6):
         g.upload(steps[1 + rep % 2])
         g.step_device(); g.sync()
         t = g.read_timing()
         r = g.results()
-        print(f"warm: build {t.build_ms:.3f} ms solve {t.solve_ms:.3f} ms -> {N/(t.build_ms+t.solve_ms)*1e3:.3e} solves/s; iters mean {r['iters'].mean():.1f} status ok {(r['status']==1).mean():.4f}")
+        print(f"warm: build {t.build_ms:.3f} ms scale {t.scale_ms:.3f} ms solve {t.solve_ms:.3f} ms -> {N/(t.build_ms+t.scale_ms+t.solve_ms)*1e3:.3e} solves/s; iters mean {r['iters'].mean():.1f} status ok {(r['status']==1).mean():.4f}")
     b = spec.algorithmic_bytes
     print("alg bytes/solve", b, "build-kernel GB/s (J+bias+targets in, H+f out):", N * 8 * (spec.s*spec.nv + 2*spec.s + spec.nv*spec.nv + spec.nv) / (t.build_ms*1e-3) / 1e9)
 
