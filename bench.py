@@ -13,8 +13,10 @@ through NSETS resident batches.
 value      whole-job solves/s with inputs resident in HBM (device-timed, max over ranks)
 e2e        same metric through the C-ABI with pinned HOST buffers: H2D of the step's
            inputs + step + D2H of the torques inside the timed region
-roofline   dominant kernel (solve_kernel): algorithmic FLOPs / CUDA-event time vs the
-           measured FP64-FMA peak; `roofline_build` is the HBM-bound build kernel
+roofline   dominant kernel (solve_kernel3 for the Walter robots: assembly, factorisation,
+           ADMM): algorithmic FLOPs / CUDA-event time vs the measured FP64-FMA peak;
+           `roofline_scale` is the equilibration kernel (FP64 pipe: mul + compare per entry
+           and pass), `roofline_build` the HBM-bound objective-build kernel
 cpu_baseline  the oracle (restatement of the reference's CPU path, "port") on the box's
            host cores, bounded sample, same protocol
 --impl reference   times that CPU path alone (rank 0 only).
@@ -63,6 +65,16 @@ def algorithmic_flops_per_solve(spec, k_mean):
     per_iter = 2 * 2 * nnzA + 2 * n * n + 12 * spec.m
     per_check = 2 * n * n + 2 * nnzA
     return setup + per_iter * k_mean + per_check * np.ceil(k_mean / 25.0)
+
+
+def scale_ops_per_solve(spec, passes=10):
+    """Equilibration kernel (OSQP scale_data): every pass takes the infinity norm of every
+    column and row of the scaled [P A'; A 0], i.e. one multiply and one compare per stored
+    entry of P and two of each per entry of A (row and column norm), all on the FP64 pipe."""
+    n, nv, nu, nc = spec.n, spec.nv, spec.nu, spec.nc
+    nnz_p = nv * nv + (n - nv)
+    nnz_a = nv * (nv + 3 * nc) + nu + 12 * nc + n
+    return passes * 2 * (nnz_p + 2 * nnz_a)
 
 
 def build_bytes_per_solve(spec):
@@ -343,17 +355,32 @@ def main():
     except Exception:
         pass
     tr = traffic.get(args.workload, {})
-    roofline = {"kernel": "solve_kernel", "bound": "fp64_fma", "achieved": solve_tflops,
+    split = kt.scale_ms > 0.0  # Walter robots: equilibration runs in its own kernel
+    solve_name = "solve_kernel3" if split else "solve_kernel"
+    roofline = {"kernel": solve_name, "bound": "fp64_fma", "achieved": solve_tflops,
                 "peak": dfma_peak, "unit": "TFLOP/s", "frac": solve_tflops / dfma_peak,
-                "traffic": tr.get("solve_kernel_dram_bytes_per_launch"),
+                "traffic": tr.get(solve_name + "_dram_bytes_per_launch"),
                 "peak_source": "DFMA micro-benchmark run inside this bench "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_solve": flops / n_envs, "iters_mean": k_mean,
-                "ncu_busiest_unit": "LSU data pipe (shared-memory wavefronts) 70 % of peak; "
-                                    "FP64 pipe 24 %, issue slots 41 % (profiles/r1d_ncu_summary.md)",
+                "ncu": "latency-bound: 8 warps/SM at 255 registers, issue slots 37 %, FP64 "
+                       "pipe 31 %, shared-memory pipe 66 % of peak (profiles/r1g_ncu_summary.md)"
+                       if split else "profiles/r1d_ncu_summary.md",
                 "launch_ms": kt.solve_ms,
-                "hbm_view": {"achieved_gbs": spec.algorithmic_bytes * n_envs / (kt.solve_ms * 1e-3) / 1e9,
+                "hbm_view": {"achieved_gbs": spec.algorithmic_bytes * n_envs
+                             / ((kt.solve_ms + kt.scale_ms) * 1e-3) / 1e9,
                              "peak_gbs": hbm_peak}}
+    roofline_scale = None
+    if split:
+        ops = scale_ops_per_solve(spec, 10) * n_envs
+        t_ops = ops / (kt.scale_ms * 1e-3) / 1e12
+        roofline_scale = {"kernel": "scale_kernel3", "bound": "fp64_pipe", "achieved": t_ops,
+                          "peak": dfma_peak / 2.0, "unit": "Tops/s (FP64 mul / compare)",
+                          "frac": t_ops / (dfma_peak / 2.0),
+                          "traffic": tr.get("scale_kernel3_dram_bytes_per_launch"),
+                          "peak_source": "half the DFMA FLOP rate: one FP64-pipe instruction "
+                                         "per lane per op",
+                          "algorithmic_ops_per_solve": ops / n_envs, "launch_ms": kt.scale_ms}
     roofline_build = {"kernel": "build_qp_kernel", "bound": "hbm", "achieved": build_gbs,
                       "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
                       "traffic": tr.get("build_qp_kernel_dram_bytes_per_launch"),
@@ -373,7 +400,10 @@ def main():
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms,
                     "wall_ms_per_step": e2e_wall_ms},
             "gpu_launches": int(stats["launches"]),
-            "roofline": roofline, "roofline_build": roofline_build,
+            "roofline": roofline, "roofline_scale": roofline_scale,
+            "roofline_build": roofline_build,
+            "kernel_ms": {"build_qp_kernel": kt.build_ms, "scale_kernel3": kt.scale_ms,
+                          solve_name: kt.solve_ms},
             "p50_batch_latency_ms": p50_ms,
             "solved_frac": stats["solved"] / (world * n_envs),
             "cold_start": {"ms_per_step": cold_ms, "value": world * n_envs / (cold_ms * 1e-3),

@@ -597,7 +597,7 @@ struct osc_handle {
   cudaEvent_t fence_ev;
   int n_counters;
   int solve_warps_pref;
-  int solve3_warps;
+  int solve3_warps, scale3_warps;
   cudaEvent_t timing_mid;  // set while a timed step is being recorded: scale | solve boundary
   int solve_core;       // 2: force the generic core (OSC_B200_SOLVE_CORE=2), else by robot shape
   int build_grid_max;   // resident CTAs of build_qp_kernel on the device
@@ -718,9 +718,8 @@ constexpr int kSolve3Warps = 8;  // 255 registers per thread; Workspace3 x 8 fit
 
 constexpr int kScale3Warps = 12;  // <= 168 registers per thread
 
-template <class D>
-int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
-  constexpr int WARPS = kScale3Warps;
+template <class D, int WARPS>
+int launch_scale3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
   const size_t smem = WARPS * sizeof(osc::RuizWorkspace<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::scale_kernel3<D, WARPS>;
   if (!h->kernels_ready)
@@ -742,6 +741,13 @@ int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;
+}
+
+template <class D>
+int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  // OSC_B200_SCALE3_WARPS=16: occupancy experiment (128 registers per thread, small spills)
+  if (h->scale3_warps == 16) return launch_scale3w<D, 16>(h, st, env0, n, counter);
+  return launch_scale3w<D, kScale3Warps>(h, st, env0, n, counter);
 }
 
 template <class D, int WARPS>
@@ -888,6 +894,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
     h->solve_core = c ? atoi(c) : 0;
     const char* w3 = getenv("OSC_B200_SOLVE3_WARPS");
     h->solve3_warps = w3 ? atoi(w3) : kSolve3Warps;
+    const char* s3 = getenv("OSC_B200_SCALE3_WARPS");
+    h->scale3_warps = s3 ? atoi(s3) : kScale3Warps;
   }
   // work counters of the solve launches [0, n), the re-Init count [n], work counters of the
   // scale launches [n + 1, 2n + 1)
