@@ -317,6 +317,8 @@ def main():
     e2e_ms = sharding.max_over_ranks(g0.elapsed_time(g1), dev) / args.steps
     e2e_wall_ms = sharding.max_over_ranks(1e3 * (time.perf_counter() - w0), dev) / args.steps
     e2e_value = world * n_envs / (e2e_ms * 1e-3)
+    # bytes the C-ABI actually moved per step (it skips Jacobian rows nothing reads)
+    e2e_h2d, e2e_d2h = osc.host_traffic()
 
     # ---- off the hot path: one all-gather of torques + statistics
     gather_ms = None
@@ -396,9 +398,10 @@ def main():
                        "inputs_exceed_l2": bool(in_bytes > 126e6),
                        "resident_input_sets": NSETS, "parallelism": f"env-sharded x{world}"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms,
-                    "wall_ms_per_step": e2e_wall_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
+                    "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms,
+                    "wall_ms_per_step": e2e_wall_ms, "host_input_bytes_per_step": in_bytes,
+                    "pcie_h2d_gbs": e2e_h2d / (e2e_ms * 1e-3) / 1e9},
             "gpu_launches": int(stats["launches"]),
             "roofline": roofline, "roofline_scale": roofline_scale,
             "roofline_build": roofline_build,

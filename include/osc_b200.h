@@ -147,10 +147,18 @@ int osc_sync(osc_handle *h, void *stream);
 int osc_download_objective(osc_handle *h, double *H_dv, double *f_dv, void *stream);
 
 /* update_state/update_taskspace_targets + control step + get_torque_command for a
- * whole batch with HOST buffers: upload, step, download torques, synchronise. */
+ * whole batch with HOST buffers: upload, step, download torques, synchronise.
+ * The upload is pipelined in chunks of environments against the kernels, and skips the rows
+ * of the task Jacobian nothing reads: rows of a (site, translational|rotational) block whose
+ * objective weight is zero and that are not contact rows (H = 2 J'WJ gives them weight 0 and
+ * contact_jacobian is the contact rows only).  Everything else goes up in full. */
 int osc_step_host(osc_handle *h, const double *M, const double *C, const double *J,
                   const double *bias, const double *targets, const double *mask, double *torque,
                   void *stream);
+
+/* Bytes the last osc_step_host moved over PCIe: host -> device (inputs) and device -> host
+ * (torques). */
+int osc_host_traffic(const osc_handle *h, size_t *h2d_bytes, size_t *d2h_bytes);
 
 /* Use caller-owned DEVICE memory as the inputs of subsequent osc_setup/osc_step calls
  * (same layouts; NULL keeps the handle's own buffer for that field).  Lets a rollout

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "osc_params.h"
@@ -598,6 +599,10 @@ struct osc_handle {
   int n_counters;
   int solve_warps_pref;
   int solve3_warps, scale3_warps;
+  // row ranges [first, last) of the task Jacobian the kernels read: rows with a non-zero
+  // objective weight plus the contact rows (= contact_jacobian'); osc_step_host uploads these
+  std::vector<std::pair<int, int>> j_rows;
+  size_t host_h2d_bytes, host_d2h_bytes;  // traffic of the last osc_step_host
   cudaEvent_t timing_mid;  // set while a timed step is being recorded: scale | solve boundary
   int solve_core;       // 2: force the generic core (OSC_B200_SOLVE_CORE=2), else by robot shape
   int build_grid_max;   // resident CTAs of build_qp_kernel on the device
@@ -907,6 +912,19 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   cudaMemset(h->dStatus, 0, N * sizeof(int));
   h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
   h->iMask = h->dMask;
+  {
+    const int S = h->s, jc0 = 3 * h->ns - 3 * h->nc, jc1 = 3 * h->ns;
+    int first = -1;
+    for (int k = 0; k <= S; ++k) {
+      const bool live = k < S && (h->params.w_row[k] != 0.0 || (k >= jc0 && k < jc1));
+      if (live && first < 0) first = k;
+      if (!live && first >= 0) {
+        h->j_rows.emplace_back(first, k);
+        first = -1;
+      }
+    }
+  }
+  h->host_h2d_bytes = h->host_d2h_bytes = 0;
   h->timing = false;
   h->timing_mid = nullptr;
   h->ev_used = 0;
@@ -1156,7 +1174,17 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
     const size_t e0 = (size_t)c * chunk;
     const size_t n = (size_t)((e0 + chunk <= (size_t)N) ? chunk : N - e0);
     cudaStream_t cs = h->copy_stream;
-    OSC_CUDA(h, cudaMemcpyAsync(h->dJ + e0 * s * nv, J + e0 * s * nv, n * s * nv * B, cudaMemcpyHostToDevice, cs));
+    // task Jacobian: only the rows the kernels read (zero-weight task rows stay behind)
+    if (h->j_rows.size() == 1 && h->j_rows[0].first == 0 && h->j_rows[0].second == (int)s) {
+      OSC_CUDA(h, cudaMemcpyAsync(h->dJ + e0 * s * nv, J + e0 * s * nv, n * s * nv * B, cudaMemcpyHostToDevice, cs));
+    } else {
+      for (const auto& r : h->j_rows) {
+        const size_t off = e0 * s * nv + (size_t)r.first * nv;
+        OSC_CUDA(h, cudaMemcpy2DAsync(h->dJ + off, s * nv * B, J + off, s * nv * B,
+                                      (size_t)(r.second - r.first) * nv * B, n,
+                                      cudaMemcpyHostToDevice, cs));
+      }
+    }
     OSC_CUDA(h, cudaMemcpyAsync(h->dM + e0 * nv * nv, M + e0 * nv * nv, n * nv * nv * B, cudaMemcpyHostToDevice, cs));
     OSC_CUDA(h, cudaMemcpyAsync(h->dBias + e0 * s, bias + e0 * s, n * s * B, cudaMemcpyHostToDevice, cs));
     OSC_CUDA(h, cudaMemcpyAsync(h->dTargets + e0 * s, targets + e0 * s, n * s * B, cudaMemcpyHostToDevice, cs));
@@ -1171,7 +1199,20 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
     OSC_CUDA(h, cudaMemcpyAsync(torque + e0 * nu, h->dTorque + e0 * nu, n * nu * B, cudaMemcpyDeviceToHost, st));
   }
   h->kernels_ready = true;
+  {
+    size_t jrows = 0;
+    for (const auto& r : h->j_rows) jrows += (size_t)(r.second - r.first);
+    h->host_h2d_bytes = (size_t)N * B * (jrows * nv + nv * nv + 2 * s + nv + nc);
+    h->host_d2h_bytes = (size_t)N * B * nu;
+  }
   OSC_CUDA(h, cudaStreamSynchronize(st));
+  return OSC_OK;
+}
+
+int osc_host_traffic(const osc_handle* h, size_t* h2d_bytes, size_t* d2h_bytes) {
+  if (!h) return OSC_ERR_INVALID;
+  if (h2d_bytes) *h2d_bytes = h->host_h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = h->host_d2h_bytes;
   return OSC_OK;
 }
 

@@ -27,7 +27,7 @@ EXPORTS = (
     "osc_download", "osc_sync", "osc_step_host", "osc_kernel_launches",
     "osc_measure_dfma_tflops", "osc_host_alloc", "osc_host_free", "osc_bind_device_inputs",
     "osc_timing_enable", "osc_timing_read", "osc_download_objective", "osc_reinit_count",
-    "osc_targets_pd", "osc_contact_mask_from_contacts",
+    "osc_targets_pd", "osc_contact_mask_from_contacts", "osc_host_traffic",
 )
 
 
@@ -108,6 +108,7 @@ def load():
     L.osc_bind_device_inputs.argtypes = [vp] + [vp] * 6
     L.osc_targets_pd.argtypes = [vp, C.POINTER(CSiteState), dp, dp, dp, dp, vp]
     L.osc_contact_mask_from_contacts.argtypes = [vp, vp, vp, C.c_int, ip, ip, vp]
+    L.osc_host_traffic.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.osc_timing_enable.argtypes = [vp, C.c_int]
     L.osc_timing_read.argtypes = [vp, C.POINTER(CKernelTimes)]
     _LIB = L
@@ -314,6 +315,12 @@ class BatchedOSC:
             self.h, geom_pairs_dev, ncon_dev, int(max_con), ids.ctypes.data_as(ip),
             sog.ctypes.data_as(ip) if sog is not None else None, stream),
             "osc_contact_mask_from_contacts")
+
+    def host_traffic(self):
+        """(h2d_bytes, d2h_bytes) of the last step() / step_host_into()."""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.L.osc_host_traffic(self.h, C.byref(a), C.byref(b)), "osc_host_traffic")
+        return a.value, b.value
 
     def enable_timing(self, on: bool = True):
         self._check(self.L.osc_timing_enable(self.h, int(on)), "osc_timing_enable")
