@@ -357,7 +357,7 @@ def main():
     except Exception:
         pass
     tr = traffic.get(args.workload, {})
-    split = kt.scale_ms > 0.0  # Walter robots: equilibration runs in its own kernel
+    split = spec.nv <= 16  # Walter robots (osc_core3): equilibration runs in its own kernel
     solve_name = "solve_kernel3" if split else "solve_kernel"
     roofline = {"kernel": solve_name, "bound": "fp64_fma", "achieved": solve_tflops,
                 "peak": dfma_peak, "unit": "TFLOP/s", "frac": solve_tflops / dfma_peak,

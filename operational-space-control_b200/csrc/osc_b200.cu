@@ -597,8 +597,6 @@ struct osc_handle {
   std::vector<cudaEvent_t> chunk_ev;
   cudaEvent_t fence_ev;
   int n_counters;
-  int solve_warps_pref;
-  int solve3_warps, scale3_warps;
   // row ranges [first, last) of the task Jacobian the kernels read: rows with a non-zero
   // objective weight plus the contact rows (= contact_jacobian'); osc_step_host uploads these
   std::vector<std::pair<int, int>> j_rows;
@@ -634,13 +632,10 @@ constexpr int max_solve_warps() {
              ? 16
              : (int)((227 * 1024 - 128) / sizeof(osc::Workspace<D>));
 }
-// Registers are allocated per SM sub-partition: 13-16 warps per CTA leave 128 registers per
-// thread, 9-12 warps leave 168.  Both variants are built; OSC_B200_SOLVE_WARPS=12|16 picks
-// one (default 12: no spills, same throughput).
+// Generic core: 9-12 warps per CTA leave 168 registers per thread (registers are allocated
+// per SM sub-partition); 16 warps at 128 registers spill and measured the same.
 template <class D>
-constexpr int solve_warps_hi() { return max_solve_warps<D>(); }
-template <class D>
-constexpr int solve_warps_lo() { return max_solve_warps<D>() > 12 ? 12 : max_solve_warps<D>(); }
+constexpr int solve_warps() { return max_solve_warps<D>() > 12 ? 12 : max_solve_warps<D>(); }
 
 template <class D>
 int launch_build(osc_handle* h, cudaStream_t st, int env0, int n) {
@@ -721,10 +716,13 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
 
 constexpr int kSolve3Warps = 8;  // 255 registers per thread; Workspace3 x 8 fits easily
 
-constexpr int kScale3Warps = 12;  // <= 168 registers per thread
+constexpr int kScale3Warps = 12;
 
-template <class D, int WARPS>
-int launch_scale3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+// 12 warps per CTA: 168 registers per thread, no spills (16 warps at 128 registers spill a
+// little and measured the same 0.17 ms)
+template <class D>
+int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  constexpr int WARPS = kScale3Warps;
   const size_t smem = WARPS * sizeof(osc::RuizWorkspace<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::scale_kernel3<D, WARPS>;
   if (!h->kernels_ready)
@@ -746,13 +744,6 @@ int launch_scale3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;
-}
-
-template <class D>
-int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
-  // OSC_B200_SCALE3_WARPS=16: occupancy experiment (128 registers per thread, small spills)
-  if (h->scale3_warps == 16) return launch_scale3w<D, 16>(h, st, env0, n, counter);
-  return launch_scale3w<D, kScale3Warps>(h, st, env0, n, counter);
 }
 
 template <class D, int WARPS>
@@ -787,8 +778,6 @@ int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   int rc = launch_scale3<D>(h, st, env0, n, counter);
   if (rc) return rc;
   if (h->timing_mid) OSC_CUDA(h, cudaEventRecord(h->timing_mid, st));
-  // OSC_B200_SOLVE3_WARPS=4: occupancy experiment (one warp per scheduler)
-  if (h->solve3_warps == 4) return launch_solve3w<D, 4>(h, st, env0, n, counter);
   return launch_solve3w<D, kSolve3Warps>(h, st, env0, n, counter);
 }
 
@@ -797,11 +786,7 @@ int launch_solve(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
   if constexpr (osc::kUseCore3<D>) {
     if (h->solve_core != 2) return launch_solve3<D>(h, st, env0, n, counter);
   }
-  if (h->solve_warps_pref == 4) return launch_solve_w<D, 4>(h, st, env0, n, counter);
-  if (h->solve_warps_pref == 8) return launch_solve_w<D, 8>(h, st, env0, n, counter);
-  if (h->solve_warps_pref == 12 || solve_warps_hi<D>() == solve_warps_lo<D>())
-    return launch_solve_w<D, solve_warps_lo<D>()>(h, st, env0, n, counter);
-  return launch_solve_w<D, solve_warps_hi<D>()>(h, st, env0, n, counter);
+  return launch_solve_w<D, solve_warps<D>()>(h, st, env0, n, counter);
 }
 
 #define OSC_DISPATCH(h, fn, ...)                                                    \
@@ -893,14 +878,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   if ((ce = cudaMalloc((void**)&h->dStatus, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   h->n_counters = 64;
   {
-    const char* e = getenv("OSC_B200_SOLVE_WARPS");
-    h->solve_warps_pref = e ? atoi(e) : 12;  // measured equal at 16 (128 regs, spills)
     const char* c = getenv("OSC_B200_SOLVE_CORE");
     h->solve_core = c ? atoi(c) : 0;
-    const char* w3 = getenv("OSC_B200_SOLVE3_WARPS");
-    h->solve3_warps = w3 ? atoi(w3) : kSolve3Warps;
-    const char* s3 = getenv("OSC_B200_SCALE3_WARPS");
-    h->scale3_warps = s3 ? atoi(s3) : kScale3Warps;
   }
   // work counters of the solve launches [0, n), the re-Init count [n], work counters of the
   // scale launches [n + 1, 2n + 1)

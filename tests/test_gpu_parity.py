@@ -458,3 +458,64 @@ def test_targets_pd_and_contact_mask_kernels_match_oracle(oracle):
     tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
     assert np.array_equal(a["iters"][keep], o["iters"][keep])
     assert (d <= tol).mean() > 0.99
+
+
+def test_step_host_uploads_only_rows_that_are_read():
+    """osc_step_host leaves the rows of the task Jacobian nothing reads on the host (zero
+    objective weight and not a contact row): the PCIe byte count drops accordingly and
+    poisoning those rows in the host buffer changes nothing."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr_true_tumbling_mjjoint")
+    n_envs = 300
+    w_row = np.concatenate([np.repeat(spec.w_trans, 3), np.repeat(spec.w_rot, 3)])
+    dead = w_row == 0.0
+    dead[3 * spec.ns - 3 * spec.nc:3 * spec.ns] = False  # contact rows are always read
+    assert dead.sum() == 12
+    s0 = ob.synth.make_inputs(spec, n_envs, "tumbling", step=0)
+    s1 = ob.synth.make_inputs(spec, n_envs, "tumbling", step=1)
+    a = capi.BatchedOSC(spec, n_envs)
+    a.setup(s0)
+    ta = a.step(s1)
+    h2d, d2h = a.host_traffic()
+    full = sum(np.asarray(s1[k]).nbytes for k in ("M", "C", "J", "bias", "targets", "mask"))
+    assert h2d == full - n_envs * int(dead.sum()) * spec.nv * 8
+    assert d2h == n_envs * spec.nu * 8
+    b = capi.BatchedOSC(spec, n_envs)
+    b.setup(s0)
+    poisoned = dict(s1, J=s1["J"].copy())
+    poisoned["J"][:, dead, :] = np.nan
+    tb = b.step(poisoned)
+    assert np.array_equal(ta, tb)
+    assert np.isfinite(tb).all()
+
+
+def test_register_resident_core_agrees_with_generic_core(monkeypatch):
+    """The Walter robots run osc_core3.cuh (scale_kernel3 + solve_kernel3); the generic core
+    (osc_core.cuh, what the Go2 runs) can be forced for them with OSC_B200_SOLVE_CORE=2.  Two
+    independent implementations of the same control step (different lane mappings, Gauss-
+    Jordan variants, summation orders): same iteration counts, torques within the tolerance."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr_wheels")
+    n_envs = 2048
+    steps = [ob.synth.make_inputs(spec, n_envs, "stairs", step=t) for t in range(3)]
+    out = {}
+    for core in ("0", "2"):
+        monkeypatch.setenv("OSC_B200_SOLVE_CORE", core)
+        g = capi.BatchedOSC(spec, n_envs)
+        g.setup(steps[0])
+        res = []
+        for inp in steps:
+            g.step(inp)
+            res.append(g.results())
+        out[core] = res
+        g.close()
+    for t in range(3):
+        a, b = out["0"][t], out["2"][t]
+        same = a["iters"] == b["iters"]
+        assert same.mean() > 0.995, (t, same.mean())
+        d = np.abs(a["torque"] - b["torque"])[same]
+        tol = (ATOL + RTOL * np.abs(b["torque"]))[same]
+        assert ((d <= tol).all(axis=1)).mean() > 0.995, (t, (d / tol).max())
+        assert np.array_equal(a["status"][same], b["status"][same])
