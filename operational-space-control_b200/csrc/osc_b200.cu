@@ -558,6 +558,39 @@ contact_mask_kernel(const __grid_constant__ ContactIds ids, const int* __restric
 }
 
 // ---------------------------------------------------------------------------
+// Self-test of the warp primitives osc_core3.cuh is written against (osc_warp.cuh): the
+// device readings of the shuffles, reductions and the DMMA tile product, to be compared
+// with the host emulation the CPU tests run the same core on.
+// in: [18][32] (rows 0-15: non-negative values for max16 / row 0 also for the shuffles and
+// the sum; row 16: A fragment, row 17: B fragment)
+// out: max16[16], sum, pad, xchg16[32], group4(r=2)[32], d0[32], d1[32]
+// ---------------------------------------------------------------------------
+__global__ void warp_selftest_kernel(const double* __restrict__ in, double* __restrict__ out) {
+  __shared__ double scratch[16];
+  const int lane0 = threadIdx.x & 31;
+  Var<double> m[16], a, b, d0, d1, x, g;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) m[q][lane0] = in[32 * q + lane0];
+  a[lane0] = in[32 * 16 + lane0];
+  b[lane0] = in[32 * 17 + lane0];
+  d0[lane0] = 1.0;
+  d1[lane0] = -1.0;
+  double r16[16];
+  Var<double> row0 = m[0];
+  Warp::max16(m, r16, scratch, lane0);
+  const double sm = Warp::sum(row0);
+  Warp::xchg16(x, row0);
+  Warp::group4(g, row0, 2);
+  Warp::mma884(d0, d1, a, b);
+  if (lane0 < 16) out[lane0] = r16[lane0];
+  if (lane0 == 0) out[16] = sm;
+  out[18 + lane0] = x[lane0];
+  out[50 + lane0] = g[lane0];
+  out[82 + lane0] = d0[lane0];
+  out[114 + lane0] = d1[lane0];
+}
+
+// ---------------------------------------------------------------------------
 // FP64 FMA peak
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -1186,6 +1219,25 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
   }
   OSC_CUDA(h, cudaStreamSynchronize(st));
   return OSC_OK;
+}
+
+int osc_selftest_warp(int device, const double* in, double* out) {
+  if (!in || !out) return OSC_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return OSC_ERR_CUDA;
+  double *din = nullptr, *dout = nullptr;
+  if (cudaMalloc((void**)&din, 18 * 32 * sizeof(double)) != cudaSuccess) return OSC_ERR_ALLOC;
+  if (cudaMalloc((void**)&dout, 146 * sizeof(double)) != cudaSuccess) {
+    cudaFree(din);
+    return OSC_ERR_ALLOC;
+  }
+  cudaMemcpy(din, in, 18 * 32 * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemset(dout, 0, 146 * sizeof(double));
+  osc::warp_selftest_kernel<<<1, 32>>>(din, dout);
+  const cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(out, dout, 146 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(din);
+  cudaFree(dout);
+  return e == cudaSuccess ? OSC_OK : OSC_ERR_CUDA;
 }
 
 int osc_host_traffic(const osc_handle* h, size_t* h2d_bytes, size_t* d2h_bytes) {

@@ -28,6 +28,7 @@ EXPORTS = (
     "osc_measure_dfma_tflops", "osc_host_alloc", "osc_host_free", "osc_bind_device_inputs",
     "osc_timing_enable", "osc_timing_read", "osc_download_objective", "osc_reinit_count",
     "osc_targets_pd", "osc_contact_mask_from_contacts", "osc_host_traffic",
+    "osc_selftest_warp",
 )
 
 
@@ -108,6 +109,7 @@ def load():
     L.osc_bind_device_inputs.argtypes = [vp] + [vp] * 6
     L.osc_targets_pd.argtypes = [vp, C.POINTER(CSiteState), dp, dp, dp, dp, vp]
     L.osc_contact_mask_from_contacts.argtypes = [vp, vp, vp, C.c_int, ip, ip, vp]
+    L.osc_selftest_warp.argtypes = [C.c_int, dp, dp]
     L.osc_host_traffic.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.osc_timing_enable.argtypes = [vp, C.c_int]
     L.osc_timing_read.argtypes = [vp, C.POINTER(CKernelTimes)]

@@ -519,3 +519,30 @@ def test_register_resident_core_agrees_with_generic_core(monkeypatch):
         tol = (ATOL + RTOL * np.abs(b["torque"]))[same]
         assert ((d <= tol).all(axis=1)).mean() > 0.995, (t, (d / tol).max())
         assert np.array_equal(a["status"][same], b["status"][same])
+
+
+def test_device_warp_primitives_match_their_host_emulation():
+    """osc_warp.cuh on the device (SHFL, the transposing 16-way max, DMMA m8n8k4) gives what
+    the host emulation -- the one tests/test_warp_emulation.py pins against numpy and
+    tests/host_core runs the solver core on -- defines."""
+    import ctypes as C
+    from osc_b200 import capi
+    L = capi.load()
+    rng = np.random.default_rng(7)
+    inp = np.abs(rng.standard_normal((18, 32)))
+    inp[16:] = rng.standard_normal((2, 32))
+    out = np.zeros(146)
+    dp = C.POINTER(C.c_double)
+    assert L.osc_selftest_warp(0, inp.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+    lanes = np.arange(32)
+    assert np.array_equal(out[:16], inp[:16].max(axis=1))
+    assert abs(out[16] - inp[0].sum()) < 1e-13
+    assert np.array_equal(out[18:50], inp[0][lanes ^ 16])
+    assert np.array_equal(out[50:82], inp[0][(lanes & ~3) | 2])
+    g, t = lanes >> 2, lanes & 3
+    A = np.zeros((8, 4)); B = np.zeros((4, 8))
+    A[g, t] = inp[16]
+    B[t, g] = inp[17]
+    R = A @ B
+    np.testing.assert_allclose(out[82:114], 1.0 + R[g, 2 * t], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(out[114:146], -1.0 + R[g, 2 * t + 1], rtol=0, atol=1e-14)
