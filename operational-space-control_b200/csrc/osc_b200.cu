@@ -747,15 +747,22 @@ int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   return OSC_OK;
 }
 
-constexpr int kSolve3Warps = 8;  // 255 registers per thread; Workspace3 x 8 fits easily
+// solve_kernel3: at most 8 warps per CTA (255 registers per thread), fewer when 8 workspaces
+// (landing stage included) do not fit in 227 KB of shared memory
+template <class D>
+constexpr int solve3_warps() {
+  constexpr int fit = (int)((227 * 1024 - 128) / sizeof(osc::Workspace3<D>));
+  return fit > 8 ? 8 : fit;
+}
+// scale_kernel3: 12 warps per CTA at 168 registers when two lanes share a row (16 warps at 128
+// registers spill a little and measured the same 0.17 ms); rows held by one lane need more
+// registers per thread: 8 warps
+template <class D>
+constexpr int scale3_warps() { return (2 * D::NV <= 32) ? 12 : 8; }
 
-constexpr int kScale3Warps = 12;
-
-// 12 warps per CTA: 168 registers per thread, no spills (16 warps at 128 registers spill a
-// little and measured the same 0.17 ms)
 template <class D>
 int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
-  constexpr int WARPS = kScale3Warps;
+  constexpr int WARPS = scale3_warps<D>();
   const size_t smem = WARPS * sizeof(osc::RuizWorkspace<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::scale_kernel3<D, WARPS>;
   if (!h->kernels_ready)
@@ -811,7 +818,7 @@ int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   int rc = launch_scale3<D>(h, st, env0, n, counter);
   if (rc) return rc;
   if (h->timing_mid) OSC_CUDA(h, cudaEventRecord(h->timing_mid, st));
-  return launch_solve3w<D, kSolve3Warps>(h, st, env0, n, counter);
+  return launch_solve3w<D, solve3_warps<D>()>(h, st, env0, n, counter);
 }
 
 template <class D>
@@ -1028,7 +1035,7 @@ int osc_step(osc_handle* h, void* stream) {
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
   // ev[2] = scale | solve boundary: recorded by launch_solve3 between its two kernels; the
   // generic core has no separate scale kernel (recorded here: scale_ms = 0)
-  const bool split = h->shape == osc::Shape::kWalter && h->solve_core != 2;
+  const bool split = h->solve_core != 2;  // both robot shapes run the register-resident core
   h->timing_mid = (ev && split) ? ev[2] : nullptr;
   if (ev && !split) OSC_CUDA(h, cudaEventRecord(ev[2], st));
   rc = OSC_DISPATCH(h, launch_solve, h, st, 0, h->n_envs, 0);
