@@ -357,8 +357,8 @@ def main():
     except Exception:
         pass
     tr = traffic.get(args.workload, {})
-    split = spec.nv <= 16  # Walter robots (osc_core3): equilibration runs in its own kernel
-    solve_name = "solve_kernel3" if split else "solve_kernel"
+    split = True  # equilibration runs in its own kernel (scale_kernel3) for every robot
+    solve_name = "solve_kernel3"
     roofline = {"kernel": solve_name, "bound": "fp64_fma", "achieved": solve_tflops,
                 "peak": dfma_peak, "unit": "TFLOP/s", "frac": solve_tflops / dfma_peak,
                 "traffic": tr.get(solve_name + "_dram_bytes_per_launch"),

@@ -8,11 +8,14 @@
 //                     mbarrier completion) through a 3-stage ring; one thread per
 //                     output entry.
 //   init_state_kernel set_up_optimization(): cold iterates, rho0, first linear cost.
-//   solve_kernel      K3: one warp per environment, persistent CTAs with a dynamic
-//                     work counter.  Loads M, H, f, C, contact rows of J, mask and the
-//                     warm-start record with TMA bulk copies into the warp's private
-//                     shared-memory workspace, then runs osc::Core::step (scaling,
-//                     factorisation, ADMM, un-scaling) entirely on chip in FP64.
+//   scale_kernel3     K3a: OSQP's scale_data (Ruiz equilibration + cost scaling) and the
+//                     update-path decision, one warp per environment, unscaled matrices in
+//                     registers for all passes (osc::Core3::ruiz).
+//   solve_kernel3     K3b: one warp per environment, persistent CTAs with a dynamic work
+//                     counter and a per-warp landing stage (the next environment's TMA bulk
+//                     copies overlap the solve of the current one): assembly, factorisation,
+//                     ADMM with register-resident matrices, un-scaling, entirely on chip in
+//                     FP64 (osc::Core3::step_prepare / step_solve).
 //   reset_warm_kernel reset_optimization().
 //   dfma_peak_kernel  FP64-FMA roofline denominator.
 //
@@ -301,60 +304,6 @@ struct SolveArgs {
   int n_envs;
 };
 
-template <class D, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-solve_kernel(const __grid_constant__ Params p, const SolveArgs a) {
-  using WS = Workspace<D>;
-  using C32 = Core<D, 32>;
-  constexpr int NV = D::NV;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  WS* wsb = reinterpret_cast<WS*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WARPS * sizeof(WS));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WS& w = wsb[warp];
-  uint64_t* bar = &bars[warp];
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
-  uint32_t parity = 0;
-  constexpr uint32_t kBytes =
-      sizeof(double) * (NV * NV + NV * NV + D::NZ * NV + D::STATE + NV + NV + D::NC);
-  for (;;) {
-    int env = 0;
-    if (lane == 0) env = atomicAdd(a.counter, 1);
-    env = __shfl_sync(0xffffffffu, env, 0);
-    if (env >= a.n_envs) break;
-    if (lane == 0) {
-      fence_proxy_async();  // order the previous environment's generic-proxy accesses
-      mbar_expect_tx(bar, kBytes);
-      bulk_g2s(w.Ae, a.M + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
-      bulk_g2s(w.Pdv, a.Hdv + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
-      bulk_g2s(w.scratch, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(double) * D::NZ * NV,
-               bar);
-      bulk_g2s(w.land, a.state + (size_t)env * D::STATE, sizeof(double) * D::STATE, bar);
-      bulk_g2s(w.Cv, a.C + (size_t)env * NV, sizeof(double) * NV, bar);
-      bulk_g2s(w.fv, a.fdv + (size_t)env * NV, sizeof(double) * NV, bar);
-      bulk_g2s(w.maskv, a.mask + (size_t)env * D::NC, sizeof(double) * D::NC, bar);
-    }
-    mbar_wait(bar, parity);
-    parity ^= 1;
-    const Result r = C32::step(w, p, lane, a.fdv + (size_t)env * NV, a.sol_x + (size_t)env * D::N,
-                               a.sol_y + (size_t)env * D::M, a.torque + (size_t)env * D::NU,
-                               a.state + (size_t)env * D::STATE);
-    if (lane == 0) {
-      a.iters[env] = r.iter;
-      a.status[env] = r.status;
-      a.pri_res[env] = r.pri_res;
-      a.dua_res[env] = r.dua_res;
-      a.rho[env] = r.rho;
-      if (r.reinit) atomicAdd(a.reinits, 1);
-    }
-    __syncwarp();
-  }
-}
-
 // K3a for robots with 2 nv <= 32: OSQP's scale_data (10 Ruiz passes) + the update-path decision
 // of update_optimization (:565-584), osc::Core3::ruiz.  Its own kernel because it needs a
 // third of the registers of the solve (more warps per SM hide its dependent max / rsqrt
@@ -635,7 +584,6 @@ struct osc_handle {
   std::vector<std::pair<int, int>> j_rows;
   size_t host_h2d_bytes, host_d2h_bytes;  // traffic of the last osc_step_host
   cudaEvent_t timing_mid;  // set while a timed step is being recorded: scale | solve boundary
-  int solve_core;       // 2: force the generic core (OSC_B200_SOLVE_CORE=2), else by robot shape
   int build_grid_max;   // resident CTAs of build_qp_kernel on the device
   bool kernels_ready;
   // optional per-kernel timing
@@ -657,18 +605,6 @@ thread_local std::string g_create_err;
       return OSC_ERR_CUDA;                                                        \
     }                                                                             \
   } while (0)
-
-template <class D>
-constexpr int max_solve_warps() {
-  // as many warps (environments) per CTA as fit in 227 KB of shared memory, at most 16
-  return (int)((227 * 1024 - 128) / sizeof(osc::Workspace<D>)) > 16
-             ? 16
-             : (int)((227 * 1024 - 128) / sizeof(osc::Workspace<D>));
-}
-// Generic core: 9-12 warps per CTA leave 168 registers per thread (registers are allocated
-// per SM sub-partition); 16 warps at 128 registers spill and measured the same.
-template <class D>
-constexpr int solve_warps() { return max_solve_warps<D>() > 12 ? 12 : max_solve_warps<D>(); }
 
 template <class D>
 int launch_build(osc_handle* h, cudaStream_t st, int env0, int n) {
@@ -715,33 +651,6 @@ int launch_reset(osc_handle* h, cudaStream_t st) {
   int grid = (int)((total + threads - 1) / threads);
   if (grid > h->sm_count * 8) grid = h->sm_count * 8;
   osc::reset_warm_kernel<D><<<grid, threads, 0, st>>>(h->dState, h->n_envs);
-  OSC_CUDA(h, cudaGetLastError());
-  h->launches++;
-  return OSC_OK;
-}
-
-template <class D, int WARPS>
-int launch_solve_w(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
-  static_assert(WARPS >= 1, "workspace does not fit in shared memory");
-  const size_t smem = WARPS * sizeof(osc::Workspace<D>) + WARPS * sizeof(uint64_t);
-  auto kern = osc::solve_kernel<D, WARPS>;
-  if (!h->kernels_ready)
-    OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = h->sm_count;
-  const int need = (n + WARPS - 1) / WARPS;
-  if (grid > need) grid = need;
-  OSC_CUDA(h, cudaMemsetAsync(h->dCounter + counter, 0, sizeof(int), st));
-  const size_t e = (size_t)env0;
-  osc::SolveArgs a;
-  a.M = h->iM + e * D::NV * D::NV; a.C = h->iC + e * D::NV; a.J = h->iJ + e * D::S * D::NV;
-  a.mask = h->iMask + e * D::NC; a.Hdv = h->dH + e * D::NV * D::NV; a.fdv = h->dF + e * D::NV;
-  a.state = h->dState + e * D::STATE;
-  a.torque = h->dTorque + e * D::NU; a.sol_x = h->dX + e * D::N; a.sol_y = h->dY + e * D::M;
-  a.pri_res = h->dPri + e; a.dua_res = h->dDua + e; a.rho = h->dRho + e;
-  a.iters = h->dIters + e; a.status = h->dStatus + e; a.counter = h->dCounter + counter;
-  a.reinits = h->dCounter + h->n_counters;  // one extra slot after the work counters
-  a.n_envs = n;
-  kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;
@@ -823,10 +732,7 @@ int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
 
 template <class D>
 int launch_solve(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
-  if constexpr (osc::kUseCore3<D>) {
-    if (h->solve_core != 2) return launch_solve3<D>(h, st, env0, n, counter);
-  }
-  return launch_solve_w<D, solve_warps<D>()>(h, st, env0, n, counter);
+  return launch_solve3<D>(h, st, env0, n, counter);
 }
 
 #define OSC_DISPATCH(h, fn, ...)                                                    \
@@ -917,10 +823,6 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   if ((ce = cudaMalloc((void**)&h->dIters, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   if ((ce = cudaMalloc((void**)&h->dStatus, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   h->n_counters = 64;
-  {
-    const char* c = getenv("OSC_B200_SOLVE_CORE");
-    h->solve_core = c ? atoi(c) : 0;
-  }
   // work counters of the solve launches [0, n), the re-Init count [n], work counters of the
   // scale launches [n + 1, 2n + 1)
   if ((ce = cudaMalloc((void**)&h->dCounter, (2 * h->n_counters + 1) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
@@ -1033,11 +935,8 @@ int osc_step(osc_handle* h, void* stream) {
   int rc = OSC_DISPATCH(h, launch_build, h, st, 0, h->n_envs);
   if (rc) return rc;
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
-  // ev[2] = scale | solve boundary: recorded by launch_solve3 between its two kernels; the
-  // generic core has no separate scale kernel (recorded here: scale_ms = 0)
-  const bool split = h->solve_core != 2;  // both robot shapes run the register-resident core
-  h->timing_mid = (ev && split) ? ev[2] : nullptr;
-  if (ev && !split) OSC_CUDA(h, cudaEventRecord(ev[2], st));
+  // ev[2] = scale | solve boundary: recorded by launch_solve3 between its two kernels
+  h->timing_mid = ev ? ev[2] : nullptr;
   rc = OSC_DISPATCH(h, launch_solve, h, st, 0, h->n_envs, 0);
   h->timing_mid = nullptr;
   if (rc) return rc;

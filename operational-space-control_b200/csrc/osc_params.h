@@ -11,11 +11,6 @@ enum class Shape { kNone, kWalter, kGo2 };
 using WalterDims = Dims<14, 8, 8, 17>;  // walter_sr, walter_sr_wheels
 using Go2Dims = Dims<18, 12, 4, 5>;     // unitree_go2
 
-// robots narrow enough for two lanes per dynamics row run the register-resident core
-// (osc_core3.cuh); wider ones the generic core (osc_core.cuh)
-template <class D>
-constexpr bool kUseCore3 = (D::NV <= 32 && D::NF <= 32);
-
 inline Shape shape_of(const osc_robot_spec& r) {
   if (r.nv == 14 && r.nu == 8 && r.nc == 8 && r.ns == 17) return Shape::kWalter;
   if (r.nv == 18 && r.nu == 12 && r.nc == 4 && r.ns == 5) return Shape::kGo2;

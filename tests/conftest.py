@@ -31,6 +31,8 @@ def host_core():
     so = os.path.join(d, "libhost_core.so")
     srcs = [os.path.join(d, "host_core.cpp"),
             os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_core.cuh"),
+            os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_core3.cuh"),
+            os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_warp.cuh"),
             os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_params.h"),
             os.path.join(ROOT, "include", "osc_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):

@@ -1,8 +1,7 @@
 // tests/host_core/host_core.cpp -- TEST HARNESS ONLY.
-// Instantiates the product's per-environment algorithm on the host so that
-// `pytest -m "not gpu"` can compare the exact code the GPU runs against the oracle:
-// csrc/osc_core3.cuh with an emulated 32-lane warp (osc_warp.cuh) for the Walter robots,
-// csrc/osc_core.cuh with LANES = 1 for the Go2.  Never linked into libosc_b200.so.
+// Instantiates the product's per-environment algorithm (csrc/osc_core3.cuh) on the host with
+// an emulated 32-lane warp (csrc/osc_warp.cuh) so that `pytest -m "not gpu"` can compare the
+// exact code the GPU runs against the oracle.  Never linked into libosc_b200.so.
 #include <cstring>
 #include <memory>
 #include <type_traits>
@@ -14,8 +13,8 @@ template <class D>
 int run(const osc::Params& p, const double* M, const double* C, const double* J,
         const double* bias, const double* targets, const double* mask, double* state, double* x,
         double* y, double* torque, int* info_i, double* info_d, double* Hdv_out, double* f_out) {
-  using Core = std::conditional_t<osc::kUseCore3<D>, osc::Core3<D>, osc::Core<D, 1>>;
-  using WSpace = std::conditional_t<osc::kUseCore3<D>, osc::Workspace3<D>, osc::Workspace<D>>;
+  using Core = osc::Core3<D>;
+  using WSpace = osc::Workspace3<D>;
   using B = osc::BuildQP<D>;
   auto ws = std::make_unique<WSpace>();
   std::memset(ws.get(), 0, sizeof(*ws));
@@ -32,14 +31,8 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
   if (Hdv_out) std::memcpy(Hdv_out, H, sizeof(H));
   if (f_out) std::memcpy(f_out, f, sizeof(f));
   if (!state) return 0;
-  double *dM, *dH, *dJc, *dLand, *dC, *dF, *dMask;
-  if constexpr (osc::kUseCore3<D>) {
-    dM = ws->in.M; dH = ws->in.H; dJc = ws->in.Jc; dLand = ws->in.land;
-    dC = ws->in.Cv; dF = ws->in.fv; dMask = ws->in.maskv;
-  } else {
-    dM = ws->Ae; dH = ws->Pdv; dJc = ws->scratch; dLand = ws->land;
-    dC = ws->Cv; dF = ws->fv; dMask = ws->maskv;
-  }
+  double *dM = ws->in.M, *dH = ws->in.H, *dJc = ws->in.Jc, *dLand = ws->in.land;
+  double *dC = ws->in.Cv, *dF = ws->in.fv, *dMask = ws->in.maskv;
   std::memcpy(dM, M, sizeof(double) * D::NV * D::NV);
   std::memcpy(dH, H, sizeof(H));
   std::memcpy(dJc, J + D::JC0 * D::NV, sizeof(double) * D::NZ * D::NV);
@@ -50,19 +43,15 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
     std::memcpy(state + D::N + 2 * D::M, f, sizeof(f));
     state[D::N + 2 * D::M + D::NV] = p.rho0;
     state[D::N + 2 * D::M + D::NV + 1] = 1.0;
-    for (int q = 0; q < D::SIG; ++q) {
-      if constexpr (osc::kUseCore3<D>)
-        state[D::SIG0 + q] = Core::as_f64(Core::sig_word(dH, dM, dJc, q, 0));
-      else
-        state[D::SIG0 + q] = Core::as_f64(Core::sig_word(*ws, q, 0));
-    }
+    for (int q = 0; q < D::SIG; ++q)
+      state[D::SIG0 + q] = Core::as_f64(Core::sig_word(dH, dM, dJc, q, 0));
     return 0;
   }
   std::memcpy(dLand, state, sizeof(double) * D::STATE);
   std::memcpy(dC, C, sizeof(double) * D::NV);
   std::memcpy(dF, f, sizeof(f));
   std::memcpy(dMask, mask, sizeof(double) * D::NC);
-  if constexpr (osc::kUseCore3<D>) {
+  {
     // the equilibration kernel's part (scale_kernel3): Ruiz passes + path decision
     auto rw = std::make_unique<osc::RuizWorkspace<D>>();
     std::memset(rw.get(), 0, sizeof(*rw));

@@ -490,37 +490,6 @@ def test_step_host_uploads_only_rows_that_are_read():
     assert np.isfinite(tb).all()
 
 
-def test_register_resident_core_agrees_with_generic_core(monkeypatch):
-    """The Walter robots run osc_core3.cuh (scale_kernel3 + solve_kernel3); the generic core
-    (osc_core.cuh, what the Go2 runs) can be forced for them with OSC_B200_SOLVE_CORE=2.  Two
-    independent implementations of the same control step (different lane mappings, Gauss-
-    Jordan variants, summation orders): same iteration counts, torques within the tolerance."""
-    import osc_b200 as ob
-    from osc_b200 import capi
-    spec = ob.load_preset("walter_sr_wheels")
-    n_envs = 2048
-    steps = [ob.synth.make_inputs(spec, n_envs, "stairs", step=t) for t in range(3)]
-    out = {}
-    for core in ("0", "2"):
-        monkeypatch.setenv("OSC_B200_SOLVE_CORE", core)
-        g = capi.BatchedOSC(spec, n_envs)
-        g.setup(steps[0])
-        res = []
-        for inp in steps:
-            g.step(inp)
-            res.append(g.results())
-        out[core] = res
-        g.close()
-    for t in range(3):
-        a, b = out["0"][t], out["2"][t]
-        same = a["iters"] == b["iters"]
-        assert same.mean() > 0.995, (t, same.mean())
-        d = np.abs(a["torque"] - b["torque"])[same]
-        tol = (ATOL + RTOL * np.abs(b["torque"]))[same]
-        assert ((d <= tol).all(axis=1)).mean() > 0.995, (t, (d / tol).max())
-        assert np.array_equal(a["status"][same], b["status"][same])
-
-
 def test_device_warp_primitives_match_their_host_emulation():
     """osc_warp.cuh on the device (SHFL, the transposing 16-way max, DMMA m8n8k4) gives what
     the host emulation -- the one tests/test_warp_emulation.py pins against numpy and

@@ -1,7 +1,8 @@
-"""CPU: the product's per-environment algorithm (csrc/osc_core.cuh), instantiated with a
-single lane on the host by tests/host_core, against the oracle.  This checks the *device
-code's* arithmetic (structured KKT elimination, scaling, rho rules, termination) without a
-GPU; the GPU tests check the same code as the kernels actually run it."""
+"""CPU: the product's per-environment algorithm (csrc/osc_core3.cuh), run by tests/host_core
+on an emulated 32-lane warp (csrc/osc_warp.cuh), against the oracle.  This checks the *device
+code's* arithmetic (structured KKT elimination, scaling, rho rules, termination, the lane
+mappings for both robot shapes) without a GPU; the GPU tests check the same code as the
+kernels actually run it."""
 import ctypes as C
 
 import numpy as np
