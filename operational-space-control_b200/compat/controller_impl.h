@@ -316,6 +316,39 @@ class BatchedController {
     std::memcpy(t.data(), &torque[(size_t)e * Traits::nu], sizeof(double) * Traits::nu);
     return t;
   }
+  // ---- roll-outs that keep targets and contact masks on the device (the step before the
+  //      path: examples/standing.cc:146-155, examples/walter_sr_true_tumbling_mjjoint.cc:523-558)
+  // task-space PD targets of every (environment, site) from DEVICE-resident site states
+  absl::Status update_taskspace_targets_pd(const osc_site_state& sites, const double* kp_lin,
+                                           const double* kd_lin, const double* kp_ang,
+                                           const double* kd_ang, void* stream = nullptr) {
+    if (!handle) return absl::InternalError(error);
+    if (osc_targets_pd(handle, &sites, kp_lin, kd_lin, kp_ang, kd_ang, stream) != OSC_OK)
+      return absl::InternalError(osc_last_error(handle));
+    return absl::OkStatus();
+  }
+  // contact mask from DEVICE-resident MuJoCo contact geom pairs
+  absl::Status update_contact_mask_from_contacts(const int* geom_pairs, const int* ncon,
+                                                 int max_con, const int* contact_geom_ids,
+                                                 const int* site_of_geom = nullptr,
+                                                 void* stream = nullptr) {
+    if (!handle) return absl::InternalError(error);
+    if (osc_contact_mask_from_contacts(handle, geom_pairs, ncon, max_con, contact_geom_ids,
+                                       site_of_geom, stream) != OSC_OK)
+      return absl::InternalError(osc_last_error(handle));
+    return absl::OkStatus();
+  }
+  // control step on the inputs resident in HBM (uploaded earlier / produced by the two calls
+  // above); torques come back to the host
+  absl::Status step_resident(void* stream = nullptr) {
+    if (!handle) return absl::InternalError(error);
+    if (osc_step(handle, stream) != OSC_OK ||
+        osc_download(handle, torque.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, stream) != OSC_OK ||
+        osc_sync(handle, stream) != OSC_OK)
+      return absl::InternalError(osc_last_error(handle));
+    return absl::OkStatus();
+  }
   osc_handle* c_handle() { return handle; }
 
  private:

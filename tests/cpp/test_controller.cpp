@@ -68,5 +68,22 @@ int main(int argc, char** argv) {
   for (int i = 0; i < model::nu_size; ++i) std::printf(" %.17g", torque2(i));
   std::printf("\n");
   result = controller.clean_up();
-  return result.ok() ? 0 : 1;
+  if (!result.ok()) return 1;
+  // the N-environment sibling: three copies of the same robot, host step then resident step
+  {
+    BatchedOperationalSpaceController batch(3);
+    if (!batch.ok()) { std::printf("batch: %s\n", batch.last_error().c_str()); return 1; }
+    for (int e = 0; e < 3; ++e) batch.set_environment(e, data, targets, state);
+    if (!batch.initialize_optimization().ok() || !batch.step().ok()) return 1;
+    auto tb = batch.get_torque_command(2);
+    std::printf("TORQUE_BATCH");
+    for (int i = 0; i < model::nu_size; ++i) std::printf(" %.17g", tb(i));
+    std::printf("\n");
+    if (!batch.step_resident().ok()) return 1;  // second control step on the resident inputs
+    auto tr = batch.get_torque_command(0);
+    std::printf("TORQUE_RESIDENT");
+    for (int i = 0; i < model::nu_size; ++i) std::printf(" %.17g", tr(i));
+    std::printf("\n");
+  }
+  return 0;
 }

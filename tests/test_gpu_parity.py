@@ -239,6 +239,13 @@ def test_cpp_controller_class_drop_in(oracle, tmp_path):
         assert (np.abs(tq - o["torque"][0]) <= tol).all(), (preset, tq, o["torque"][0])
         tq2 = np.array([float(v) for v in lines["TORQUE_THREAD"]])
         assert np.isfinite(tq2).all() and np.abs(tq2 - tq).max() < 1.0 + 0.1 * np.abs(tq).max()
+        # BatchedOperationalSpaceController: same first step bit for bit, then a warm resident step
+        tb = np.array([float(v) for v in lines["TORQUE_BATCH"]])
+        assert np.array_equal(tb, tq), (preset, tb, tq)
+        o2 = b.step(inp)
+        tr = np.array([float(v) for v in lines["TORQUE_RESIDENT"]])
+        tol2 = ATOL + RTOL * np.abs(o2["torque"][0])
+        assert (np.abs(tr - o2["torque"][0]) <= tol2).all(), (preset, tr, o2["torque"][0])
 
 
 @pytest.mark.parametrize("preset,config", [("walter_sr_true_tumbling_mjjoint", "tumbling"),
