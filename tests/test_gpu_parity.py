@@ -522,3 +522,33 @@ def test_device_warp_primitives_match_their_host_emulation():
     R = A @ B
     np.testing.assert_allclose(out[82:114], 1.0 + R[g, 2 * t], rtol=0, atol=1e-14)
     np.testing.assert_allclose(out[114:146], -1.0 + R[g, 2 * t + 1], rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_wheels", "stairs"),
+                                           ("unitree_go2", "go2_standing")])
+@pytest.mark.parametrize("kw", [dict(scaling=0), dict(adaptive_rho=0), dict(warm_start=0),
+                                dict(check_termination=10), dict(alpha=1.0, rho=1.0),
+                                dict(check_termination=0, max_iter=60)],
+                         ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_settings_variants_on_device(oracle, preset, config, kw):
+    """OsqpSettings other than the defaults through the C-ABI on the GPU (the CPU suite runs
+    the larger matrix of variants on the host emulation of the same source)."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    n_envs = 256
+    steps = [ob.synth.make_inputs(spec, n_envs, config, step=t) for t in range(2)]
+    ref = _oracle_steps(oracle, spec, n_envs, steps, **kw)
+    g = capi.BatchedOSC(spec, n_envs, capi.default_settings(**kw))
+    g.setup(steps[0])
+    for t, inp in enumerate(steps):
+        g.step(inp)
+        r = g.results()
+        o = ref[t]
+        keep = o["repro"]
+        assert keep.mean() > 0.97, (kw, keep.mean())
+        assert np.array_equal(r["iters"][keep], o["iters"][keep]), (kw, t)
+        assert np.array_equal(r["status"][keep], o["status"][keep]), (kw, t)
+        d = np.abs(r["torque"] - o["torque"])[keep]
+        tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
+        assert (d <= tol).all(), (kw, t, (d / tol).max())

@@ -121,3 +121,46 @@ def test_sparsity_change_branch_matches_oracle(oracle, host_core, preset, config
         np.testing.assert_array_equal(got[t]["iters"], ref[t]["iters"])
         d = np.abs(got[t]["torque"] - ref[t]["torque"])
         assert (d <= ATOL + RTOL * np.abs(ref[t]["torque"])).all(), (t, d.max())
+
+
+SETTINGS_VARIANTS = [
+    dict(scaling=0),
+    dict(scaling=3),
+    dict(adaptive_rho=0),
+    dict(warm_start=0),
+    dict(check_termination=10),
+    dict(alpha=1.0, rho=1.0),
+    dict(check_termination=0, max_iter=60),
+    dict(adaptive_rho_interval=25, eps_abs=1e-5, eps_rel=1e-5),
+    dict(sigma=1e-4, max_iter=40),
+]
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_wheels", "stairs"),
+                                           ("unitree_go2", "go2_standing")])
+@pytest.mark.parametrize("kw", SETTINGS_VARIANTS, ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_settings_variants_match_oracle(oracle, host_core, preset, config, kw):
+    """OsqpSettings other than the defaults (the reference passes the struct through, :110):
+    scaling passes, rho adaptation on/off and its interval, warm start off, termination-check
+    interval (incl. never), relaxation, step sizes, iteration cap -- device code vs oracle."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    N = 12
+    steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(2)]
+    b = oracle.OracleBatch(spec, N, oracle.default_settings(**kw))
+    b.setup(steps[0])
+    ref = [b.step(s) for s in steps]
+    st = capi.CSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 5.0, 10, 1, 0, 4000, 25, 1)
+    for k, v in kw.items():
+        setattr(st, k, v)
+    got = run_host_core(host_core, spec, st, steps, N)
+    for t in range(2):
+        o, g = ref[t], got[t]
+        keep = o["margin"] > 1e-7
+        assert keep.mean() > 0.8
+        np.testing.assert_array_equal(g["iters"][keep], o["iters"][keep])
+        np.testing.assert_array_equal(g["status"][keep], o["status"][keep])
+        d = np.abs(g["torque"] - o["torque"])[keep]
+        tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
+        assert (d <= tol).all(), (preset, kw, t, (d / tol).max())
