@@ -552,3 +552,20 @@ def test_settings_variants_on_device(oracle, preset, config, kw):
         d = np.abs(r["torque"] - o["torque"])[keep]
         tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
         assert (d <= tol).all(), (kw, t, (d / tol).max())
+
+
+def test_examples_run(tmp_path):
+    """examples/: the device-resident Python roll-out and the batched C++ standing driver."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "rollout_device_resident.py"),
+                          "512", "5"], check=True, capture_output=True, text=True).stdout
+    assert "solves/s" in out and "solved 1.000" in out, out
+    pkg = os.path.join(ROOT, "operational-space-control_b200")
+    exe = tmp_path / "standing_batched"
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "standing_batched.cc"), "-o", str(exe),
+                    "-L", pkg, "-losc_b200", f"-Wl,-rpath,{pkg}"], check=True)
+    out = subprocess.run([str(exe), "64"], check=True, capture_output=True, text=True).stdout
+    assert "torque command of robot 0" in out, out
