@@ -107,7 +107,14 @@ struct Var {
   T& operator[](int l) { return v[l]; }
   const T& operator[](int l) const { return v[l]; }
 };
+// OSC_WARP_REVERSE runs the lanes of every body in the opposite order: a body in which one
+// lane reads what another lane writes (a race on the GPU) then gives different results, which
+// tests/test_host_core.py checks for
+#ifdef OSC_WARP_REVERSE
+#define OSC_LANES(l) for (int l = 31; l >= 0; --l)
+#else
 #define OSC_LANES(l) for (int l = 0; l < 32; ++l)
+#endif
 
 struct Warp {
   static void sync() {}

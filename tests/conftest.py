@@ -41,6 +41,17 @@ def host_core():
     return C.CDLL(so)
 
 
+@pytest.fixture(scope="session")
+def host_core_reversed(tmp_path_factory):
+    """The same harness with the emulated lanes of every body run in the opposite order."""
+    import ctypes as C
+    d = os.path.join(ROOT, "tests", "host_core")
+    so = os.path.join(str(tmp_path_factory.mktemp("hc_rev")), "libhost_core_rev.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                    "-DOSC_WARP_REVERSE", "-o", so, os.path.join(d, "host_core.cpp")], check=True)
+    return C.CDLL(so)
+
+
 def has_gpu():
     try:
         import torch
