@@ -47,9 +47,14 @@ enum {
 
 /* per-environment solver status, OSQP's values (osqp/include/constants.h) */
 enum {
-  OSC_SOLVED = 1,
+  OSC_DUAL_INFEASIBLE_INACCURATE = 4,
+  OSC_PRIMAL_INFEASIBLE_INACCURATE = 3,
   OSC_SOLVED_INACCURATE = 2,
+  OSC_SOLVED = 1,
   OSC_MAX_ITER_REACHED = -2,
+  OSC_PRIMAL_INFEASIBLE = -3, /* as in OSQP: solution / torque of that environment are NaN */
+  OSC_DUAL_INFEASIBLE = -4,   /* and its iterates restart from zero at the next step      */
+  OSC_NON_CVX = -7,
   OSC_UNSOLVED = -10
 };
 
@@ -83,6 +88,7 @@ typedef struct {
   int max_iter;
   int check_termination;
   int warm_start;
+  double eps_prim_inf, eps_dual_inf; /* infeasibility certificates (util.c is_*_infeasible) */
 } osc_settings;
 
 typedef struct osc_handle osc_handle;

@@ -50,6 +50,8 @@ inline osc_settings to_c_settings(const osqp::OsqpSettings& s) {
   c.max_iter = static_cast<int>(s.max_iter);
   c.check_termination = static_cast<int>(s.check_termination);
   c.warm_start = s.warm_start ? 1 : 0;
+  c.eps_prim_inf = s.eps_prim_inf;
+  c.eps_dual_inf = s.eps_dual_inf;
   return c;
 }
 

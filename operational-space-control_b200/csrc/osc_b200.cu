@@ -767,7 +767,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   osc_settings st;
   if (settings) st = *settings; else osc::default_settings(&st);
   if (st.max_iter < 1 || st.check_termination < 0 || st.scaling < 0 || st.rho <= 0 ||
-      st.sigma <= 0 || st.alpha <= 0 || st.alpha >= 2) {
+      st.sigma <= 0 || st.alpha <= 0 || st.alpha >= 2 || st.eps_prim_inf <= 0 ||
+      st.eps_dual_inf <= 0) {
     g_create_err = "osc_create: invalid settings";
     return OSC_ERR_INVALID;
   }

@@ -40,6 +40,8 @@ inline Params make_params(const osc_robot_spec& r, const osc_settings& s) {
   p.eps_abs = s.eps_abs;
   p.eps_rel = s.eps_rel;
   p.rho_tol = s.adaptive_rho_tolerance;
+  p.eps_prim_inf = s.eps_prim_inf;
+  p.eps_dual_inf = s.eps_dual_inf;
   p.scaling = s.scaling;
   p.adaptive_rho = s.adaptive_rho;
   p.adaptive_rho_interval = s.adaptive_rho_interval;
@@ -62,6 +64,8 @@ inline void default_settings(osc_settings* s) {
   s->max_iter = 4000;
   s->check_termination = 25;
   s->warm_start = 1;
+  s->eps_prim_inf = 1e-4;
+  s->eps_dual_inf = 1e-4;
 }
 
 }  // namespace osc

@@ -49,7 +49,16 @@ class CSettings(C.Structure):
         ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("adaptive_rho_tolerance", C.c_double),
         ("scaling", C.c_int), ("adaptive_rho", C.c_int), ("adaptive_rho_interval", C.c_int),
         ("max_iter", C.c_int), ("check_termination", C.c_int), ("warm_start", C.c_int),
+        ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
     ]
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        # OsqpSettings() defaults for the two trailing fields when built positionally
+        if len(args) < 13 and "eps_prim_inf" not in kw:
+            self.eps_prim_inf = 1e-4
+        if len(args) < 14 and "eps_dual_inf" not in kw:
+            self.eps_dual_inf = 1e-4
 
 
 class CDeviceBuffers(C.Structure):

@@ -9,6 +9,10 @@
 #include "../../operational-space-control_b200/csrc/osc_params.h"
 
 namespace {
+// added to the linear cost after the objective build: lets a test hand the solver a cost the
+// controller API cannot produce (f outside the range of H -> dual infeasible QP)
+double g_f_offset[32] = {0};
+
 template <class D>
 int run(const osc::Params& p, const double* M, const double* C, const double* J,
         const double* bias, const double* targets, const double* mask, double* state, double* x,
@@ -26,7 +30,7 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
       H[a * D::NV + b] = v;
       H[b * D::NV + a] = v;
     }
-    f[a] = B::f_entry(J, bias, targets, p.w_row, a);
+    f[a] = B::f_entry(J, bias, targets, p.w_row, a) + g_f_offset[a];
   }
   if (Hdv_out) std::memcpy(Hdv_out, H, sizeof(H));
   if (f_out) std::memcpy(f_out, f, sizeof(f));
@@ -82,6 +86,10 @@ extern "C" int osc_core_host_state_size(const osc_robot_spec* spec) {
     case osc::Shape::kGo2: return osc::Go2Dims::STATE;
     default: return -1;
   }
+}
+
+extern "C" void osc_core_host_set_f_offset(const double* df, int n) {
+  for (int a = 0; a < 32; ++a) g_f_offset[a] = (df && a < n) ? df[a] : 0.0;
 }
 
 // state == NULL: only build H (nv*nv) and f (nv).

@@ -602,3 +602,41 @@ def test_long_horizon_parity(oracle, preset, config):
     assert g.reinit_count() == 0
     print(f"{preset}: {T} steps, {alive.mean():.3f} of the environments reproducible throughout, "
           f"worst |dtau|/tol {worst:.3g}")
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr", "tumbling"), ("unitree_go2", "go2_standing")])
+def test_primal_infeasible_environments_on_device(oracle, preset, config):
+    """OSQP's primal infeasibility certificate in the solve kernel (same scenario as the host
+    test): every other environment gets a QP without a feasible point at step 1 -- status -3,
+    NaN torque / solution -- and, after the re-Init from that NaN solution (:571-584), reports
+    "solved" with NaN outputs like the reference would.  The other environments of the batch
+    are unaffected."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    n_envs = 128
+    steps = [{k: v.copy() for k, v in ob.synth.make_inputs(spec, n_envs, config, step=t).items()}
+             for t in range(4)]
+    s = steps[1]
+    s["M"][::2, 0, :] = 0
+    s["M"][::2, :, 0] = 0
+    s["mask"][::2] = 0
+    s["C"][::2, 0] = 1e4
+    b = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    b.setup(steps[0])
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(steps[0])
+    for t, inp in enumerate(steps):
+        o = b.step(inp)
+        g.step(inp)
+        r = g.results()
+        keep = (o["margin"] > 1e-6) | (o["status"] < 0) | np.isnan(o["torque"]).any(axis=1)
+        assert np.array_equal(r["status"][keep], o["status"][keep]), t
+        assert np.array_equal(r["iters"][keep], o["iters"][keep]), t
+        assert np.array_equal(np.isnan(r["torque"]), np.isnan(o["torque"])), t
+        fin = ~np.isnan(o["torque"]) & keep[:, None]
+        d = np.abs(r["torque"] - o["torque"])[fin]
+        assert (d <= (ATOL + RTOL * np.abs(o["torque"]))[fin]).all(), (t, d.max())
+        if t == 1:
+            assert (o["status"][::2] == -3).all() and (o["status"][1::2] == 1).all()
+    assert np.isnan(r["torque"][::2]).all() and not np.isnan(r["torque"][1::2]).any()

@@ -188,3 +188,121 @@ def test_no_cross_lane_hazard_inside_a_body(host_core, host_core_reversed, prese
             assert np.array_equal(a[t][k], b[t][k]), (preset, t, k)
     assert (a[0]["rho"] != 0.1).any()      # rho updates + refactorisations happened
     assert a[1]["reinit"].sum() == N // 2  # and so did the re-Init path
+
+
+def _infeasible_steps(ob, spec, config, N):
+    """Step 1 of the even environments is primal infeasible: a zero row/column in the mass
+    matrix of an unactuated dof, no contacts, a large bias force on that dof (0 = -C_0)."""
+    steps = [{k: v.copy() for k, v in ob.synth.make_inputs(spec, N, config, step=t).items()}
+             for t in range(4)]
+    s = steps[1]
+    s["M"][::2, 0, :] = 0
+    s["M"][::2, :, 0] = 0
+    s["mask"][::2] = 0
+    s["C"][::2, 0] = 1e4
+    return steps
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr", "tumbling"), ("unitree_go2", "go2_standing")])
+def test_primal_infeasibility_certificate_matches_oracle(oracle, host_core, preset, config):
+    """OSQP's primal infeasibility certificate (util.c is_primal_infeasible) and what follows
+    it in the reference: status -3, NaN solution / torque (store_solution), then -- because the
+    data's sparsity pattern changes back -- a re-Init warm started from that NaN solution
+    (:571-584), whose norms ignore NaN (vec_norm_inf), so the environment reports "solved" with
+    NaN torques from then on.  Same on the device code, while its neighbours are untouched."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    N = 8
+    steps = _infeasible_steps(ob, spec, config, N)
+    b = oracle.OracleBatch(spec, N, oracle.default_settings())
+    b.setup(steps[0])
+    ref = [b.step(s) for s in steps]
+    assert (ref[1]["status"][::2] == -3).all() and (ref[1]["status"][1::2] == 1).all()
+    st = capi.CSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 5.0, 10, 1, 0, 4000, 25, 1)
+    got = run_host_core(host_core, spec, st, steps, N)
+    for t in range(4):
+        o, g = ref[t], got[t]
+        np.testing.assert_array_equal(g["status"], o["status"])
+        np.testing.assert_array_equal(g["iters"], o["iters"])
+        np.testing.assert_array_equal(np.isnan(g["torque"]), np.isnan(o["torque"]))
+        np.testing.assert_array_equal(np.isnan(g["y"]), np.isnan(o["y"]))
+        fin = ~np.isnan(o["torque"])
+        d = np.abs(g["torque"] - o["torque"])[fin]
+        assert (d <= (ATOL + RTOL * np.abs(o["torque"]))[fin]).all(), (preset, t, d.max())
+    assert np.isnan(ref[3]["torque"][::2]).all() and not np.isnan(ref[3]["torque"][1::2]).any()
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_wheels", "stairs"), ("unitree_go2", "go2_standing")])
+def test_infeasible_step_on_the_update_path_recovers_like_oracle(oracle, host_core, preset, config):
+    """Same sparsity pattern throughout (osqp_update_P_A path): an infeasible step leaves NaN
+    outputs and zeroed iterates (store_solution -> cold_start), the next feasible step solves
+    from cold with the rho the infeasible solve ended with."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    N = 6
+    steps = [{k: v.copy() for k, v in ob.synth.make_inputs(spec, N, config, step=t).items()}
+             for t in range(4)]
+    for t, s in enumerate(steps):
+        s["M"][:, 0, :] = 0
+        s["M"][:, :, 0] = 0
+        s["mask"][:] = 0
+        s["C"][:, 0] = 0.0
+    steps[2]["C"][:3, 0] = 1e4
+    b = oracle.OracleBatch(spec, N, oracle.default_settings())
+    b.setup(steps[0])
+    ref = [b.step(s) for s in steps]
+    assert [r["reinits"] for r in ref] == [0, 0, 0, 0]
+    assert (ref[2]["status"][:3] == -3).all() and (ref[3]["status"] == 1).all()
+    st = capi.CSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 5.0, 10, 1, 0, 4000, 25, 1)
+    got = run_host_core(host_core, spec, st, steps, N)
+    for t in range(4):
+        o, g = ref[t], got[t]
+        keep = (o["margin"] > 1e-7) | (o["status"] < 0)
+        np.testing.assert_array_equal(g["status"][keep], o["status"][keep])
+        np.testing.assert_array_equal(g["iters"][keep], o["iters"][keep])
+        np.testing.assert_array_equal(np.isnan(g["torque"]), np.isnan(o["torque"]))
+        fin = ~np.isnan(o["torque"]) & keep[:, None]
+        d = np.abs(g["torque"] - o["torque"])[fin]
+        assert (d <= (ATOL + RTOL * np.abs(o["torque"]))[fin]).all(), (preset, t, d.max())
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr", "tumbling"), ("unitree_go2", "go2_standing")])
+def test_dual_infeasibility_certificate_matches_oracle(oracle, host_core, preset, config):
+    """OSQP's dual infeasibility certificate (util.c is_dual_infeasible).  The controller's own
+    linear cost always lies in the range of H, so its QP is never unbounded; the harness adds
+    an offset to f on a dof that H, M and J leave free (regularisation 0) to get one, and the
+    oracle solves the same matrices through orc_setup / orc_solve."""
+    import dataclasses
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = dataclasses.replace(ob.load_preset(preset), w_reg=0.0)
+    N = 4
+    k = 1  # an unactuated dof
+    inp = {kk: v.copy() for kk, v in ob.synth.make_inputs(spec, N, config, step=0).items()}
+    inp["M"][:, k, :] = 0
+    inp["M"][:, :, k] = 0
+    inp["J"][:, :, k] = 0
+    inp["C"][:, k] = 0
+    df = np.zeros(spec.nv)
+    df[k] = -1.0
+    ref = []
+    for e in range(N):
+        H, f, A, lo, hi = oracle.build_qp(spec, *[np.ascontiguousarray(inp[kk][e]) for kk in FIELDS])
+        f = f.copy()
+        f[:spec.nv] += df
+        ref.append(oracle.solve_qp(H, f, A, lo, hi,
+                                   oracle.default_settings(eps_abs=1e-7, eps_rel=1e-7)))
+    assert all(r["status"] == -4 for r in ref), [r["status"] for r in ref]
+    # (tolerances tight enough that the certificate fires before the growing iterates pass
+    # the relative residual test)
+    st = capi.CSettings(0.1, 1e-6, 1.6, 1e-7, 1e-7, 5.0, 10, 1, 0, 4000, 25, 1)
+    host_core.osc_core_host_set_f_offset(_p(df), spec.nv)
+    try:
+        got = run_host_core(host_core, spec, st, [inp], N)[0]
+    finally:
+        host_core.osc_core_host_set_f_offset(None, 0)
+    np.testing.assert_array_equal(got["status"], [r["status"] for r in ref])
+    np.testing.assert_array_equal(got["iters"], [r["iter"] for r in ref])
+    assert np.isnan(got["torque"]).all() and np.isnan(got["x"]).all()

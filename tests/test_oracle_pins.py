@@ -61,6 +61,12 @@ def test_osqp_restatement_small_known_answers(oracle):
     r = oracle.solve_qp(np.eye(2), [1.0, -1.0], np.eye(2), [-1e40, -1e40], [1e40, 0.25],
                         oracle.default_settings(eps_abs=1e-9, eps_rel=1e-9))
     np.testing.assert_allclose(r["x"], [-1.0, 0.25], atol=1e-7)
+    # x >= 1 and x <= 0: primal infeasible (status -3), NaN solution (store_solution)
+    r = oracle.solve_qp([[1.0]], [0.0], [[1.0], [1.0]], [1.0, -1e40], [1e40, 0.0])
+    assert r["status"] == -3 and np.isnan(r["x"]).all() and np.isnan(r["y"]).all()
+    # min -x, x >= 0, no curvature: unbounded below = dual infeasible (status -4)
+    r = oracle.solve_qp([[0.0]], [-1.0], [[1.0]], [0.0], [1e40])
+    assert r["status"] == -4 and np.isnan(r["x"]).all()
 
 
 # --------------------------------------------------------------------------- 2
