@@ -31,6 +31,19 @@
 #include <utility>
 #include <vector>
 
+#ifdef OSC_PHASE_CLOCKS  // developer build only (tools/phase_clocks.py)
+__device__ unsigned long long g_phase_clocks[16];
+__host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
+#if defined(__CUDA_ARCH__)
+  if (lane0 == 0) atomicAdd(&g_phase_clocks[k], (unsigned long long)clock64());
+#else
+  (void)k;
+  (void)lane0;
+#endif
+}
+#define OSC_TICK(k) osc_tick(k, lane0)
+#endif
+
 #include "osc_params.h"
 
 namespace osc {
@@ -418,13 +431,18 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   while (env < a.n_envs) {
     mbar_wait(bar, parity);
     parity ^= 1;
+    const int lane0 = lane;
+    (void)lane0;
+    OSC_TICK(0);
     typename C3::Regs L;
     double* sx = a.sol_x + (size_t)env * D::N;
     double* sy = a.sol_y + (size_t)env * D::M;
     double* so = a.state + (size_t)env * D::STATE;
     const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy);
     __syncwarp();
+    OSC_TICK(1);
     const int next = fetch();
+    OSC_TICK(2);
     const Result r = C3::step_solve(w, p, L, lane, pr, a.fdv + (size_t)env * NV, sx, sy,
                                     a.torque + (size_t)env * D::NU, so);
     if (lane == 0) {
@@ -436,6 +454,7 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
       if (r.reinit) atomicAdd(a.reinits, 1);
     }
     __syncwarp();
+    OSC_TICK(8);
     env = next;
   }
 }
@@ -1127,6 +1146,18 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
   OSC_CUDA(h, cudaStreamSynchronize(st));
   return OSC_OK;
 }
+
+#ifdef OSC_PHASE_CLOCKS
+int osc_debug_phase_clocks(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, ::g_phase_clocks, 16 * sizeof(unsigned long long)) != cudaSuccess)
+    return OSC_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(::g_phase_clocks, z, sizeof(z)) != cudaSuccess) return OSC_ERR_CUDA;
+  }
+  return OSC_OK;
+}
+#endif
 
 int osc_selftest_warp(int device, const double* in, double* out) {
   if (!in || !out) return OSC_ERR_INVALID;

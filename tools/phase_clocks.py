@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""Developer probe: where a solve_kernel3 warp spends its cycles.  Builds a variant of the
+library with -DOSC_PHASE_CLOCKS (sums of clock64() at phase boundaries, tools/_build/, not the
+product), runs cold and warm steps and prints cycles per environment per phase.
+usage: phase_clocks.py [preset config n_envs]"""
+import ctypes as C
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "operational-space-control_b200", "python"))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+
+def build():
+    import __graft_entry__ as g
+    out = os.path.join(ROOT, "tools", "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libosc_b200_phase.so")
+    src = os.path.join(g.PKG, "csrc", "osc_b200.cu")
+    deps = [src] + [os.path.join(g.PKG, "csrc", f) for f in ("osc_core.cuh", "osc_core3.cuh", "osc_warp.cuh")]
+    if g._newer(lib, deps):
+        subprocess.run(["nvcc", *g.NVCC_FLAGS, "-DOSC_PHASE_CLOCKS", "-o", lib, src], check=True)
+    return lib
+
+
+def main():
+    if "--build-only" in sys.argv:
+        print(build())
+        return
+    import osc_b200 as ob
+    from osc_b200 import capi
+    capi.LIB_PATH = build()
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    preset = args[0] if len(args) > 0 else "walter_sr_true_tumbling_mjjoint"
+    config = args[1] if len(args) > 1 else "tumbling"
+    N = int(args[2]) if len(args) > 2 else 16384
+    spec = ob.load_preset(preset)
+    L = capi.load()
+    L.osc_debug_phase_clocks.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(3)]
+    g = capi.BatchedOSC(spec, N)
+    g.enable_timing(True)
+    buf = (C.c_ulonglong * 16)()
+
+    def report(tag):
+        L.osc_debug_phase_clocks(buf, 1)
+        t = np.array(list(buf), dtype=np.uint64).astype(np.int64)  # wrap-around differences
+        d = lambda a, b: float(np.int64(t[a] - t[b])) / N
+        r = g.results()
+        kt = g.read_timing()
+        rows = [("prepare (assemble, iterates)", d(1, 0)), ("fetch next (TMA issue)", d(2, 1)),
+                ("set_rho + factor", d(3, 2)), ("  Kd build", d(9, 2)), ("  Kd_dv^-1 (sweep)", d(10, 9)),
+                ("  W products", d(11, 10)), ("  S product", d(12, 11)), ("  S^-1 + register loads", d(3, 12)),
+                ("iterations", d(5, 4)), ("residuals", d(6, 5)), ("termination / rho update", d(7, 6)),
+                ("whole solve part", d(8, 2)), ("environment total (excl. wait)", d(8, 0))]
+        print(f"--- {tag}: solve kernel {kt.solve_ms:.3f} ms, iters mean {r['iters'].mean():.1f}")
+        for k, v in rows:
+            print(f"  {k:34s} {v:10.0f} cycles/env")
+        it = r["iters"].mean()
+        print(f"  cycles per iteration               {d(5, 4) / it:10.0f}")
+
+    g.setup(steps[0]); g.step_device(); g.sync(); L.osc_debug_phase_clocks(buf, 1)
+    g.setup(steps[0]); g.step_device(); g.sync(); report("cold")
+    for rep in range(2):
+        g.upload(steps[1 + rep % 2]); g.step_device(); g.sync(); report("warm")
+
+
+if __name__ == "__main__":
+    main()
