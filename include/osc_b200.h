@@ -165,10 +165,11 @@ int osc_step_host(osc_handle *h, const double *M, const double *C, const double 
 /* Self-test of the warp primitives the register-resident solver core is written against
  * (csrc/osc_warp.cuh): runs the shuffles, the 16-way transposing max, the warp sum and one FP64
  * tensor-core tile product on `in` ([18][32] doubles: rows 0-15 non-negative values, row 16 an
- * mma.m8n8k4 A fragment, row 17 a B fragment) and returns, in `out` (146 doubles): max16[16],
+ * mma.m8n8k4 A fragment, row 17 a B fragment) and returns, in `out` (154 doubles): max16[16],
  * sum(row 0), 0, xchg16(row 0)[32], group4(row 0, 2)[32], and the D fragments d0[32], d1[32]
- * of D = A B + D0 with D0 = (+1, -1).  tests/ compare it with the host emulation of the same
- * primitives (what lets the CPU suite run the device solver source). */
+ * of D = A B + D0 with D0 = (+1, -1), and the 8-way max of rows 0-7.  tests/ compare it with
+ * the host emulation of the same primitives (what lets the CPU suite run the device solver
+ * source). */
 int osc_selftest_warp(int device, const double *in, double *out);
 
 /* Bytes the last osc_step_host moved over PCIe: host -> device (inputs) and device -> host

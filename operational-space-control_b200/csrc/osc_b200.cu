@@ -406,29 +406,29 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
                     sizeof(double) * (2 * NV * NV + D::NZ * NV + D::STATE + 2 * NV + D::NC +
                                       C3::SCAL),
                 "the landing stage is exactly the eight bulk copies");
-  // lane 0: draw the next environment and start landing it (returns the index to all lanes)
-  auto fetch = [&]() -> int {
-    int env = 0;
-    if (lane == 0) {
-      env = atomicAdd(a.counter, 1);
-      if (env < a.n_envs) {
-        fence_proxy_async();  // the stage's generic-proxy reads are ordered before the copies
-        mbar_expect_tx(bar, kBytes);
-        bulk_g2s(w.in.M, a.M + (size_t)env * NV * NV, sizeof(w.in.M), bar);
-        bulk_g2s(w.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(w.in.H), bar);
-        bulk_g2s(w.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(w.in.Jc), bar);
-        bulk_g2s(w.in.land, a.state + (size_t)env * D::STATE, sizeof(w.in.land), bar);
-        bulk_g2s(w.in.Cv, a.C + (size_t)env * NV, sizeof(w.in.Cv), bar);
-        bulk_g2s(w.in.fv, a.fdv + (size_t)env * NV, sizeof(w.in.fv), bar);
-        bulk_g2s(w.in.maskv, a.mask + (size_t)env * D::NC, sizeof(w.in.maskv), bar);
-        bulk_g2s(w.in.scal, a.scal + (size_t)env * C3::SCAL, sizeof(w.in.scal), bar);
-      }
+  // lane 0 draws the next environment from the work counter (`draw`: issued early, the
+  // round trip of the atomic overlaps step_prepare) and later starts landing it (`land`:
+  // eight bulk copies into the stage; returns the index to all lanes)
+  auto draw = [&]() -> int { return lane == 0 ? atomicAdd(a.counter, 1) : 0; };
+  auto land = [&](int env) -> int {
+    if (lane == 0 && env < a.n_envs) {
+      fence_proxy_async();  // the stage's generic-proxy reads are ordered before the copies
+      mbar_expect_tx(bar, kBytes);
+      bulk_g2s(w.in.M, a.M + (size_t)env * NV * NV, sizeof(w.in.M), bar);
+      bulk_g2s(w.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(w.in.H), bar);
+      bulk_g2s(w.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(w.in.Jc), bar);
+      bulk_g2s(w.in.land, a.state + (size_t)env * D::STATE, sizeof(w.in.land), bar);
+      bulk_g2s(w.in.Cv, a.C + (size_t)env * NV, sizeof(w.in.Cv), bar);
+      bulk_g2s(w.in.fv, a.fdv + (size_t)env * NV, sizeof(w.in.fv), bar);
+      bulk_g2s(w.in.maskv, a.mask + (size_t)env * D::NC, sizeof(w.in.maskv), bar);
+      bulk_g2s(w.in.scal, a.scal + (size_t)env * C3::SCAL, sizeof(w.in.scal), bar);
     }
     return __shfl_sync(0xffffffffu, env, 0);
   };
   uint32_t parity = 0;
-  int env = fetch();
+  int env = land(draw());
   while (env < a.n_envs) {
+    const int drawn = draw();
     mbar_wait(bar, parity);
     parity ^= 1;
     const int lane0 = lane;
@@ -441,7 +441,7 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy);
     __syncwarp();
     OSC_TICK(1);
-    const int next = fetch();
+    const int next = land(drawn);
     OSC_TICK(2);
     const Result r = C3::step_solve(w, p, L, lane, pr, a.fdv + (size_t)env * NV, sx, sy,
                                     a.torque + (size_t)env * D::NU, so);
@@ -531,7 +531,7 @@ contact_mask_kernel(const __grid_constant__ ContactIds ids, const int* __restric
 // with the host emulation the CPU tests run the same core on.
 // in: [18][32] (rows 0-15: non-negative values for max16 / row 0 also for the shuffles and
 // the sum; row 16: A fragment, row 17: B fragment)
-// out: max16[16], sum, pad, xchg16[32], group4(r=2)[32], d0[32], d1[32]
+// out: max16[16], sum, pad, xchg16[32], group4(r=2)[32], d0[32], d1[32], maxn<8>[8] (rows 0-7)
 // ---------------------------------------------------------------------------
 __global__ void warp_selftest_kernel(const double* __restrict__ in, double* __restrict__ out) {
   __shared__ double scratch[16];
@@ -543,9 +543,14 @@ __global__ void warp_selftest_kernel(const double* __restrict__ in, double* __re
   b[lane0] = in[32 * 17 + lane0];
   d0[lane0] = 1.0;
   d1[lane0] = -1.0;
-  double r16[16];
+  double r16[16], r8[8];
   Var<double> row0 = m[0];
+  Var<double> m8[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) m8[q] = m[q];
   Warp::max16(m, r16, scratch, lane0);
+  __syncwarp();
+  Warp::maxn<8>(m8, r8, scratch, lane0);
   const double sm = Warp::sum(row0);
   Warp::xchg16(x, row0);
   Warp::group4(g, row0, 2);
@@ -556,6 +561,7 @@ __global__ void warp_selftest_kernel(const double* __restrict__ in, double* __re
   out[50 + lane0] = g[lane0];
   out[82 + lane0] = d0[lane0];
   out[114 + lane0] = d1[lane0];
+  if (lane0 < 8) out[146 + lane0] = r8[lane0];
 }
 
 // ---------------------------------------------------------------------------
@@ -1164,15 +1170,15 @@ int osc_selftest_warp(int device, const double* in, double* out) {
   if (cudaSetDevice(device) != cudaSuccess) return OSC_ERR_CUDA;
   double *din = nullptr, *dout = nullptr;
   if (cudaMalloc((void**)&din, 18 * 32 * sizeof(double)) != cudaSuccess) return OSC_ERR_ALLOC;
-  if (cudaMalloc((void**)&dout, 146 * sizeof(double)) != cudaSuccess) {
+  if (cudaMalloc((void**)&dout, 154 * sizeof(double)) != cudaSuccess) {
     cudaFree(din);
     return OSC_ERR_ALLOC;
   }
   cudaMemcpy(din, in, 18 * 32 * sizeof(double), cudaMemcpyHostToDevice);
-  cudaMemset(dout, 0, 146 * sizeof(double));
+  cudaMemset(dout, 0, 154 * sizeof(double));
   osc::warp_selftest_kernel<<<1, 32>>>(din, dout);
   const cudaError_t e = cudaDeviceSynchronize();
-  cudaMemcpy(out, dout, 146 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out, dout, 154 * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(din);
   cudaFree(dout);
   return e == cudaSuccess ? OSC_OK : OSC_ERR_CUDA;

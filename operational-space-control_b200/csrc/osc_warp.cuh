@@ -62,32 +62,42 @@ struct Warp {
     return v;
   }
   static OSC_HD unsigned ballot(const Var<bool>& p) { return __ballot_sync(kFull, p.v); }
-  // Warp-wide maxima of 16 non-negative quantities at once: a transposing butterfly (every
-  // level halves the number of quantities a lane carries: 8+4+2+1+1 = 16 shuffles instead of
-  // 16 x 5), after which lane l holds quantity (l >> 1) & 15; the results go through `scratch`
-  // (16 doubles of shared memory) to `out`, which every lane receives.
-  static OSC_HD void max16(Var<double> (&m)[16], double* out, double* scratch, int lane) {
-    double v[16];
+  // Warp-wide maxima of NQ (8 or 16) non-negative quantities at once: a transposing butterfly
+  // (every level halves the number of quantities a lane carries: 8+4+2+1+1 = 16 shuffles for
+  // 16 quantities instead of 16 x 5, 4+2+1+1+1 = 9 for 8), after which lane l holds quantity
+  // l / (32 / NQ); the results go through `scratch` (NQ doubles of shared memory) to `out`,
+  // which every lane receives.
+  template <int NQ>
+  static OSC_HD void maxn(Var<double> (&m)[NQ], double* out, double* scratch, int lane) {
+    static_assert(NQ == 8 || NQ == 16, "quantities per reduction");
+    constexpr int G = 32 / NQ;  // lanes that end up with the same quantity
+    double v[NQ];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = m[q].v;
+    for (int q = 0; q < NQ; ++q) v[q] = m[q].v;
 #pragma unroll
-    for (int h = 8; h >= 1; h >>= 1) {  // h = quantities kept; partner offset = 2 h
-      const bool up = (lane & (2 * h)) != 0;
+    for (int h = NQ / 2; h >= 1; h >>= 1) {  // h = quantities kept; partner offset = G h
+      const bool up = (lane & (G * h)) != 0;
 #pragma unroll
       for (int q = 0; q < h; ++q) {
         const double keep = up ? v[q + h] : v[q];
         const double send = up ? v[q] : v[q + h];
-        const double t = __shfl_xor_sync(kFull, send, 2 * h);
+        const double t = __shfl_xor_sync(kFull, send, G * h);
         v[q] = t > keep ? t : keep;
       }
     }
-    const double t = __shfl_xor_sync(kFull, v[0], 1);
-    v[0] = t > v[0] ? t : v[0];
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) {
+      const double t = __shfl_xor_sync(kFull, v[0], o);
+      v[0] = t > v[0] ? t : v[0];
+    }
     __syncwarp();
-    if (!(lane & 1)) scratch[lane >> 1] = v[0];
+    if (!(lane & (G - 1))) scratch[lane / G] = v[0];
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 16; ++q) out[q] = scratch[q];
+    for (int q = 0; q < NQ; ++q) out[q] = scratch[q];
+  }
+  static OSC_HD void max16(Var<double> (&m)[16], double* out, double* scratch, int lane) {
+    maxn<16>(m, out, scratch, lane);
   }
   // FP64 tensor-core tile product D(8x8) += A(8x4) B(4x8), PTX fragment layout of
   // mma.sync.m8n8k4.f64: lane = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
@@ -148,12 +158,16 @@ struct Warp {
       if (p.v[l]) b |= 1u << l;
     return b;
   }
-  static void max16(Var<double> (&m)[16], double* out, double* scratch, int) {
-    for (int q = 0; q < 16; ++q) {
+  template <int NQ>
+  static void maxn(Var<double> (&m)[NQ], double* out, double* scratch, int) {
+    for (int q = 0; q < NQ; ++q) {
       double v = m[q].v[0];
       for (int l = 1; l < 32; ++l) v = m[q].v[l] > v ? m[q].v[l] : v;
       out[q] = scratch[q] = v;
     }
+  }
+  static void max16(Var<double> (&m)[16], double* out, double* scratch, int) {
+    maxn<16>(m, out, scratch, 0);
   }
   static void mma884(Var<double>& d0, Var<double>& d1, const Var<double>& a,
                      const Var<double>& b) {

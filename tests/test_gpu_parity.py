@@ -507,11 +507,12 @@ def test_device_warp_primitives_match_their_host_emulation():
     rng = np.random.default_rng(7)
     inp = np.abs(rng.standard_normal((18, 32)))
     inp[16:] = rng.standard_normal((2, 32))
-    out = np.zeros(146)
+    out = np.zeros(154)
     dp = C.POINTER(C.c_double)
     assert L.osc_selftest_warp(0, inp.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
     lanes = np.arange(32)
     assert np.array_equal(out[:16], inp[:16].max(axis=1))
+    assert np.array_equal(out[146:154], inp[:8].max(axis=1))
     assert abs(out[16] - inp[0].sum()) < 1e-13
     assert np.array_equal(out[18:50], inp[0][lanes ^ 16])
     assert np.array_equal(out[50:82], inp[0][(lanes & ~3) | 2])

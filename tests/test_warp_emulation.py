@@ -19,6 +19,7 @@ double wsum(const double* in) { Var<double> a; for (int l = 0; l < 32; ++l) a[l]
 double wmax(const double* in) { Var<double> a; for (int l = 0; l < 32; ++l) a[l] = in[l]; return Warp::max(a); }
 unsigned ballot(const int* in) { Var<bool> a; for (int l = 0; l < 32; ++l) a[l] = in[l] != 0; return Warp::ballot(a); }
 void max16(const double* in /*[16][32]*/, double* out) { Var<double> m[16]; double sc[16]; for (int q = 0; q < 16; ++q) for (int l = 0; l < 32; ++l) m[q][l] = in[32 * q + l]; Warp::max16(m, out, sc, 0); }
+void max8(const double* in /*[8][32]*/, double* out) { Var<double> m[8]; double sc[8]; for (int q = 0; q < 8; ++q) for (int l = 0; l < 32; ++l) m[q][l] = in[32 * q + l]; Warp::maxn<8>(m, out, sc, 0); }
 void mma(const double* a, const double* b, double* d0, double* d1) {
   Var<double> A, B, D0, D1;
   for (int l = 0; l < 32; ++l) { A[l] = a[l]; B[l] = b[l]; D0[l] = d0[l]; D1[l] = d1[l]; }
@@ -65,6 +66,9 @@ def test_shuffles_and_reductions(lib):
     o16 = np.zeros(16)
     lib.max16(_p(m), _p(o16))
     assert np.array_equal(o16, m.max(axis=1))
+    o8 = np.zeros(8)
+    lib.max8(_p(m), _p(o8))
+    assert np.array_equal(o8, m[:8].max(axis=1))
 
 
 def test_mma_fragment_layout(lib):
