@@ -48,7 +48,9 @@ def main():
         d = lambda a, b: float(np.int64(t[a] - t[b])) / N
         r = g.results()
         kt = g.read_timing()
-        rows = [("prepare (assemble, iterates)", d(1, 0)), ("fetch next (TMA issue)", d(2, 1)),
+        rows = [("prepare (assemble, iterates)", d(1, 0)), ("  scaling record -> D, E", d(13, 0)),
+                ("  scale P, Aeq", d(14, 13)), ("  bounds, cost, pyramid", d(15, 14)),
+                ("  iterates, rest", d(1, 15)), ("fetch next (TMA issue)", d(2, 1)),
                 ("set_rho + factor", d(3, 2)), ("  Kd build", d(9, 2)), ("  Kd_dv^-1 (sweep)", d(10, 9)),
                 ("  W products", d(11, 10)), ("  S product", d(12, 11)), ("  S^-1 + register loads", d(3, 12)),
                 ("iterations", d(5, 4)), ("residuals", d(6, 5)), ("termination / rho update", d(7, 6)),
