@@ -365,8 +365,8 @@ def main():
                 "peak_source": "DFMA micro-benchmark run inside this bench "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_solve": flops / n_envs, "iters_mean": k_mean,
-                "ncu": "latency-bound: 8 warps/SM at 255 registers, issue slots 40 %, FP64 "
-                       "pipe 32 %, shared-memory pipe 62 % of peak (profiles/r1p_ncu_summary.md)",
+                "ncu": "latency-bound: 8 warps/SM at 255 registers, issue slots 37 %, FP64 "
+                       "pipe 33 %, shared-memory pipe 67 % of peak (profiles/r1q_ncu_summary.md)",
                 "launch_ms": kt.solve_ms,
                 "hbm_view": {"achieved_gbs": spec.algorithmic_bytes * n_envs
                              / ((kt.solve_ms + kt.scale_ms) * 1e-3) / 1e9,
