@@ -641,3 +641,37 @@ def test_primal_infeasible_environments_on_device(oracle, preset, config):
         if t == 1:
             assert (o["status"][::2] == -3).all() and (o["status"][1::2] == 1).all()
     assert np.isnan(r["torque"][::2]).all() and not np.isnan(r["torque"][1::2]).any()
+
+
+@pytest.mark.timeout(120)
+def test_non_finite_inputs_do_not_hang_or_leak_into_other_environments(oracle):
+    """NaN / Inf in the data of a few environments (a diverged simulation upstream): the warp
+    of such an environment must stay converged (its reductions are NaN-safe: vec_norm_inf
+    semantics) and finish; every other environment of the batch is solved as usual."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr")
+    n_envs = 96
+    steps = [{k: v.copy() for k, v in ob.synth.make_inputs(spec, n_envs, "tumbling", step=t).items()}
+             for t in range(3)]
+    bad = np.array([3, 17, 40, 41, 95])
+    steps[1]["M"][3, 2, 2] = np.nan
+    steps[1]["J"][17, 5, 1] = np.inf
+    steps[1]["C"][40, :] = np.nan
+    steps[1]["targets"][41] = -np.inf
+    steps[1]["mask"][95, 0] = np.nan
+    good = np.setdiff1d(np.arange(n_envs), bad)
+    b = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    b.setup(steps[0])
+    g = capi.BatchedOSC(spec, n_envs)
+    g.setup(steps[0])
+    for t, inp in enumerate(steps):
+        o = b.step(inp)
+        g.step(inp)
+        r = g.results()
+        keep = good[o["margin"][good] > 1e-6]
+        assert np.array_equal(r["iters"][keep], o["iters"][keep]), t
+        assert np.array_equal(r["status"][keep], o["status"][keep]), t
+        d = np.abs(r["torque"] - o["torque"])[keep]
+        assert (d <= (ATOL + RTOL * np.abs(o["torque"]))[keep]).all(), (t, d.max())
+        assert (r["iters"] >= 1).all() and (r["iters"] <= 4000).all()
