@@ -32,7 +32,7 @@
 #include <vector>
 
 #ifdef OSC_PHASE_CLOCKS  // developer build only (tools/phase_clocks.py)
-__device__ unsigned long long g_phase_clocks[16];
+__device__ unsigned long long g_phase_clocks[24];
 __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 #if defined(__CUDA_ARCH__)
   if (lane0 == 0) atomicAdd(&g_phase_clocks[k], (unsigned long long)clock64());
@@ -438,13 +438,13 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     double* sx = a.sol_x + (size_t)env * D::N;
     double* sy = a.sol_y + (size_t)env * D::M;
     double* so = a.state + (size_t)env * D::STATE;
-    const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy);
+    const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy, so);
     __syncwarp();
     OSC_TICK(1);
     const int next = land(drawn);
     OSC_TICK(2);
-    const Result r = C3::step_solve(w, p, L, lane, pr, a.fdv + (size_t)env * NV, sx, sy,
-                                    a.torque + (size_t)env * D::NU, so);
+    const Result r =
+        C3::step_solve(w, p, L, lane, pr, sx, sy, a.torque + (size_t)env * D::NU, so);
     if (lane == 0) {
       a.iters[env] = r.iter;
       a.status[env] = r.status;
@@ -1155,10 +1155,10 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
 
 #ifdef OSC_PHASE_CLOCKS
 int osc_debug_phase_clocks(unsigned long long* out16, int reset) {
-  if (cudaMemcpyFromSymbol(out16, ::g_phase_clocks, 16 * sizeof(unsigned long long)) != cudaSuccess)
+  if (cudaMemcpyFromSymbol(out16, ::g_phase_clocks, 24 * sizeof(unsigned long long)) != cudaSuccess)
     return OSC_ERR_CUDA;
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[24] = {0};
     if (cudaMemcpyToSymbol(::g_phase_clocks, z, sizeof(z)) != cudaSuccess) return OSC_ERR_CUDA;
   }
   return OSC_OK;

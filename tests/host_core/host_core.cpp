@@ -68,7 +68,7 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
     // (the solve kernel lands the state record after the equilibration kernel ran)
     std::memcpy(dLand, state, sizeof(double) * D::STATE);
   }
-  osc::Result r = Core::step(*ws, p, 0, f, x, y, torque, state);
+  osc::Result r = Core::step(*ws, p, 0, x, y, torque, state);
   info_i[0] = r.iter;
   info_i[1] = r.status;
   info_i[2] = r.rho_updates;

@@ -40,7 +40,7 @@ def main():
     steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(3)]
     g = capi.BatchedOSC(spec, N)
     g.enable_timing(True)
-    buf = (C.c_ulonglong * 16)()
+    buf = (C.c_ulonglong * 24)()
 
     def report(tag):
         L.osc_debug_phase_clocks(buf, 1)
@@ -54,7 +54,7 @@ def main():
                 ("set_rho + factor", d(3, 2)), ("  Kd build", d(9, 2)), ("  Kd_dv^-1 (sweep)", d(10, 9)),
                 ("  W products", d(11, 10)), ("  S product", d(12, 11)), ("  S^-1 + register loads", d(3, 12)),
                 ("iterations", d(5, 4)), ("residuals", d(6, 5)), ("termination / rho update", d(7, 6)),
-                ("whole solve part", d(8, 2)), ("environment total (excl. wait)", d(8, 0))]
+                ("outputs", d(8, 16)), ("whole solve part", d(8, 2)), ("environment total (excl. wait)", d(8, 0))]
         print(f"--- {tag}: solve kernel {kt.solve_ms:.3f} ms, iters mean {r['iters'].mean():.1f}")
         for k, v in rows:
             print(f"  {k:34s} {v:10.0f} cycles/env")
