@@ -5,8 +5,8 @@
 //   build_qp_kernel   K2: objective matrices H (dv block) and f from J, bias, targets.
 //                     HBM-bound stream: every environment's J/bias/targets record is
 //                     pulled into shared memory by 1-D TMA bulk copies (cp.async.bulk,
-//                     mbarrier completion) through a 3-stage ring; one thread per
-//                     output entry.
+//                     mbarrier completion) through a 2-stage ring per warp; the products
+//                     J'WJ and J'W(bias - t) run on the FP64 tensor cores (DMMA).
 //   init_state_kernel set_up_optimization(): cold iterates, rho0, first linear cost.
 //   scale_kernel3     K3a: OSQP's scale_data (Ruiz equilibration + cost scaling) and the
 //                     update-path decision, one warp per environment, unscaled matrices in
@@ -17,6 +17,11 @@
 //                     ADMM with register-resident matrices, un-scaling, entirely on chip in
 //                     FP64 (osc::Core3::step_prepare / step_solve).
 //   reset_warm_kernel reset_optimization().
+//   targets_pd_kernel, contact_mask_kernel
+//                     the step before the path for device-resident roll-outs: task-space PD
+//                     targets and contact masks.
+//   warp_selftest_kernel
+//                     the device reading of the warp primitives of osc_warp.cuh (tests).
 //   dfma_peak_kernel  FP64-FMA roofline denominator.
 //
 // No CPU fallback exists in this library.
