@@ -529,7 +529,10 @@ def test_device_warp_primitives_match_their_host_emulation():
                                            ("unitree_go2", "go2_standing")])
 @pytest.mark.parametrize("kw", [dict(scaling=0), dict(adaptive_rho=0), dict(warm_start=0),
                                 dict(check_termination=10), dict(alpha=1.0, rho=1.0),
-                                dict(check_termination=0, max_iter=60)],
+                                dict(check_termination=0, max_iter=60),
+                                dict(adaptive_rho_interval=30, eps_abs=1e-6, eps_rel=1e-6),
+                                dict(check_termination=7, adaptive_rho_interval=10, max_iter=45,
+                                     eps_abs=1e-7, eps_rel=1e-7)],
                          ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
 def test_settings_variants_on_device(oracle, preset, config, kw):
     """OsqpSettings other than the defaults through the C-ABI on the GPU (the CPU suite runs

@@ -133,6 +133,12 @@ SETTINGS_VARIANTS = [
     dict(check_termination=0, max_iter=60),
     dict(adaptive_rho_interval=25, eps_abs=1e-5, eps_rel=1e-5),
     dict(sigma=1e-4, max_iter=40),
+    # events that do not line up: rho adaptation between termination checks, a budget that
+    # ends between both (the stretches of the ADMM loop end at whichever comes first)
+    dict(adaptive_rho_interval=30, eps_abs=1e-6, eps_rel=1e-6),
+    dict(check_termination=7, adaptive_rho_interval=10, max_iter=45, eps_abs=1e-7, eps_rel=1e-7),
+    dict(check_termination=25, adaptive_rho_interval=25, max_iter=25),
+    dict(max_iter=1),
 ]
 
 
