@@ -157,7 +157,10 @@ int osc_download_objective(osc_handle *h, double *H_dv, double *f_dv, void *stre
  * The upload is pipelined in chunks of environments against the kernels, and skips the rows
  * of the task Jacobian nothing reads: rows of a (site, translational|rotational) block whose
  * objective weight is zero and that are not contact rows (H = 2 J'WJ gives them weight 0 and
- * contact_jacobian is the contact rows only).  Everything else goes up in full. */
+ * contact_jacobian is the contact rows only).  Everything else goes up in full.
+ * A handle of a few robots (inputs <= 128 KiB: the reference's own one-robot 1 kHz loop) takes a
+ * low-latency route instead: the inputs are staged in one pinned slab, uploaded with a single
+ * copy on `stream`, and the torques return through pinned memory. */
 int osc_step_host(osc_handle *h, const double *M, const double *C, const double *J,
                   const double *bias, const double *targets, const double *mask, double *torque,
                   void *stream);

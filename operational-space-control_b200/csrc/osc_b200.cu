@@ -316,8 +316,12 @@ struct SolveArgs {
   double* state;
   double *torque, *sol_x, *sol_y, *pri_res, *dua_res, *rho;
   int *iters, *status;
-  const double* scal;  // scaling records of scale_kernel3 (Core3 path only)
-  int* counter;
+  const double* scal;  // scaling records of scale_kernel3
+  // work counter: never reset -- a launch over n environments with W warps draws exactly
+  // n + W tickets (every warp draws one past the end), so the host knows where the next
+  // launch's tickets start (`base`) without a memset between the kernels
+  unsigned* counter;
+  unsigned base;
   int* reinits;
   int n_envs;
 };
@@ -331,7 +335,8 @@ struct ScaleArgs {
   const double *M, *J, *Hdv, *fdv;
   double* state;  // reads previous f / flag / signature, updates the signature in place
   double* scal;   // out: D, E, c, path flag per environment
-  int* counter;
+  unsigned* counter;  // see SolveArgs
+  unsigned base;
   int n_envs;
 };
 
@@ -359,7 +364,7 @@ scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
   auto fetch = [&]() -> int {
     int env = 0;
     if (lane == 0) {
-      env = atomicAdd(a.counter, 1);
+      env = (int)(atomicAdd(a.counter, 1u) - a.base);
       if (env < a.n_envs) {
         fence_proxy_async();
         mbar_expect_tx(bar, kBytes);
@@ -414,7 +419,9 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   // lane 0 draws the next environment from the work counter (`draw`: issued early, the
   // round trip of the atomic overlaps step_prepare) and later starts landing it (`land`:
   // eight bulk copies into the stage; returns the index to all lanes)
-  auto draw = [&]() -> int { return lane == 0 ? atomicAdd(a.counter, 1) : 0; };
+  auto draw = [&]() -> int {
+    return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0;
+  };
   auto land = [&](int env) -> int {
     if (lane == 0 && env < a.n_envs) {
       fence_proxy_async();  // the stage's generic-proxy reads are ordered before the copies
@@ -597,11 +604,17 @@ struct osc_handle {
   bool setup_done;
   // sizes per environment (doubles)
   int nv, nu, nc, ns, n, m, s, state;
-  // device buffers
+  // device buffers; the six inputs are carved from one slab (dIn) so that a small batch can be
+  // uploaded with a single copy (osc_step_host's few-robot path)
+  double *dIn;
+  size_t in_doubles;                  // slab size
+  size_t in_off[6];                   // M, C, J, bias, targets, mask (doubles)
+  double *hIn, *hTq;                  // pinned staging of that path (allocated on first use)
   double *dM, *dC, *dJ, *dBias, *dTargets, *dMask;
   double *dH, *dF, *dState, *dScal;
   double *dTorque, *dX, *dY, *dPri, *dDua, *dRho;
   int *dIters, *dStatus, *dCounter;
+  std::vector<unsigned> ctr_base;  // first ticket of the next launch on every work counter
   // inputs actually read by the kernels (own buffers unless osc_bind_device_inputs)
   const double *iM, *iC, *iJ, *iBias, *iTargets, *iMask;
   // pipelined host path: copy stream + per-chunk events and work counters
@@ -709,18 +722,19 @@ int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   int grid = h->sm_count;
   const int need = (n + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
-  int* ctr = h->dCounter + h->n_counters + 1 + counter;  // second bank of work counters
-  OSC_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(int), st));
+  const int slot = h->n_counters + 1 + counter;  // second bank of work counters
   const size_t e = (size_t)env0;
   osc::ScaleArgs a;
   a.M = h->iM + e * D::NV * D::NV; a.J = h->iJ + e * D::S * D::NV;
   a.Hdv = h->dH + e * D::NV * D::NV; a.fdv = h->dF + e * D::NV;
   a.state = h->dState + e * D::STATE;
   a.scal = h->dScal + e * osc::Core3<D>::SCAL;
-  a.counter = ctr;
+  a.counter = reinterpret_cast<unsigned*>(h->dCounter) + slot;
+  a.base = h->ctr_base[slot];
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
+  h->ctr_base[slot] += (unsigned)n + (unsigned)(grid * WARPS);
   h->launches++;
   return OSC_OK;
 }
@@ -734,7 +748,6 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   int grid = h->sm_count;
   const int need = (n + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
-  OSC_CUDA(h, cudaMemsetAsync(h->dCounter + counter, 0, sizeof(int), st));
   const size_t e = (size_t)env0;
   osc::SolveArgs a;
   a.M = h->iM + e * D::NV * D::NV; a.C = h->iC + e * D::NV; a.J = h->iJ + e * D::S * D::NV;
@@ -742,12 +755,15 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   a.state = h->dState + e * D::STATE;
   a.torque = h->dTorque + e * D::NU; a.sol_x = h->dX + e * D::N; a.sol_y = h->dY + e * D::M;
   a.pri_res = h->dPri + e; a.dua_res = h->dDua + e; a.rho = h->dRho + e;
-  a.iters = h->dIters + e; a.status = h->dStatus + e; a.counter = h->dCounter + counter;
+  a.iters = h->dIters + e; a.status = h->dStatus + e;
+  a.counter = reinterpret_cast<unsigned*>(h->dCounter) + counter;
+  a.base = h->ctr_base[counter];
   a.reinits = h->dCounter + h->n_counters;
   a.scal = h->dScal + e * osc::Core3<D>::SCAL;
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
+  h->ctr_base[counter] += (unsigned)n + (unsigned)(grid * WARPS);
   h->launches++;
   return OSC_OK;
 }
@@ -841,9 +857,22 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   }
   h->sm_count = prop.multiProcessorCount;
   const size_t N = (size_t)n_envs;
+  {
+    const size_t sz[6] = {N * h->nv * h->nv, N * h->nv, N * h->s * h->nv, N * h->s, N * h->s,
+                          N * h->nc};
+    size_t off = 0;
+    for (int k = 0; k < 6; ++k) {
+      h->in_off[k] = off;
+      off += (sz[k] + 31) & ~(size_t)31;  // 256-byte aligned regions
+    }
+    h->in_doubles = off;
+    if ((ce = cudaMalloc((void**)&h->dIn, off * sizeof(double))) != cudaSuccess) return fail(ce, "cudaMalloc");
+    if ((ce = cudaMemset(h->dIn, 0, off * sizeof(double))) != cudaSuccess) return fail(ce, "cudaMemset");
+    h->dM = h->dIn + h->in_off[0]; h->dC = h->dIn + h->in_off[1]; h->dJ = h->dIn + h->in_off[2];
+    h->dBias = h->dIn + h->in_off[3]; h->dTargets = h->dIn + h->in_off[4];
+    h->dMask = h->dIn + h->in_off[5];
+  }
   struct { double** p; size_t n; } bufs[] = {
-      {&h->dM, N * h->nv * h->nv}, {&h->dC, N * h->nv}, {&h->dJ, N * h->s * h->nv},
-      {&h->dBias, N * h->s}, {&h->dTargets, N * h->s}, {&h->dMask, N * h->nc},
       {&h->dH, N * h->nv * h->nv}, {&h->dF, N * h->nv}, {&h->dState, N * h->state},
       {&h->dTorque, N * h->nu}, {&h->dX, N * h->n}, {&h->dY, N * h->m},
       {&h->dPri, N}, {&h->dDua, N}, {&h->dRho, N}, {&h->dScal, N * (size_t)(h->n + h->m + 2)}};
@@ -860,6 +889,7 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");
   if ((ce = cudaEventCreateWithFlags(&h->fence_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
   cudaMemset(h->dCounter, 0, (2 * h->n_counters + 1) * sizeof(int));
+  h->ctr_base.assign(2 * h->n_counters + 1, 0u);
   cudaMemset(h->dIters, 0, N * sizeof(int));
   cudaMemset(h->dStatus, 0, N * sizeof(int));
   h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
@@ -889,9 +919,11 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
 int osc_destroy(osc_handle* h) {
   if (!h) return OSC_ERR_INVALID;
   cudaSetDevice(h->device);
-  double* d[] = {h->dM, h->dC, h->dJ, h->dBias, h->dTargets, h->dMask, h->dH, h->dF, h->dState,
+  double* d[] = {h->dIn, h->dH, h->dF, h->dState,
                  h->dTorque, h->dX, h->dY, h->dPri, h->dDua, h->dRho, h->dScal};
   for (double* p : d) if (p) cudaFree(p);
+  if (h->hIn) cudaFreeHost(h->hIn);
+  if (h->hTq) cudaFreeHost(h->hTq);
   if (h->dIters) cudaFree(h->dIters);
   if (h->dStatus) cudaFree(h->dStatus);
   if (h->dCounter) cudaFree(h->dCounter);
@@ -1082,6 +1114,44 @@ int osc_sync(osc_handle* h, void* stream) {
   return OSC_OK;
 }
 
+// A few robots (the reference's own use: one robot in a 1 kHz loop): the whole input slab is
+// staged in pinned memory and uploaded with ONE copy on the caller's stream, the torques come
+// back through pinned memory -- a dozen driver calls fewer than the chunked pipeline, which
+// is what such a step's latency consists of.
+constexpr size_t kFewRobotsBytes = 128 * 1024;
+static int step_host_few(osc_handle* h, const double* M, const double* C, const double* J,
+                         const double* bias, const double* targets, const double* mask,
+                         double* torque, cudaStream_t st) {
+  const size_t B = sizeof(double), N = (size_t)h->n_envs;
+  const size_t nv = h->nv, s = h->s, nc = h->nc, nu = h->nu;
+  if (!h->hIn) {
+    OSC_CUDA(h, cudaHostAlloc((void**)&h->hIn, h->in_doubles * B, cudaHostAllocDefault));
+    std::memset(h->hIn, 0, h->in_doubles * B);
+    OSC_CUDA(h, cudaHostAlloc((void**)&h->hTq, N * nu * B, cudaHostAllocDefault));
+  }
+  std::memcpy(h->hIn + h->in_off[0], M, N * nv * nv * B);
+  std::memcpy(h->hIn + h->in_off[1], C, N * nv * B);
+  for (size_t e = 0; e < N; ++e)  // only the rows the kernels read leave the caller's buffer
+    for (const auto& r : h->j_rows)
+      std::memcpy(h->hIn + h->in_off[2] + (e * s + (size_t)r.first) * nv,
+                  J + (e * s + (size_t)r.first) * nv, (size_t)(r.second - r.first) * nv * B);
+  std::memcpy(h->hIn + h->in_off[3], bias, N * s * B);
+  std::memcpy(h->hIn + h->in_off[4], targets, N * s * B);
+  std::memcpy(h->hIn + h->in_off[5], mask, N * nc * B);
+  OSC_CUDA(h, cudaMemcpyAsync(h->dIn, h->hIn, h->in_doubles * B, cudaMemcpyHostToDevice, st));
+  int rc = OSC_DISPATCH(h, launch_build, h, st, 0, (int)N);
+  if (rc) return rc;
+  rc = OSC_DISPATCH(h, launch_solve, h, st, 0, (int)N, 0);
+  if (rc) return rc;
+  OSC_CUDA(h, cudaMemcpyAsync(h->hTq, h->dTorque, N * nu * B, cudaMemcpyDeviceToHost, st));
+  h->kernels_ready = true;
+  h->host_h2d_bytes = h->in_doubles * B;
+  h->host_d2h_bytes = N * nu * B;
+  OSC_CUDA(h, cudaStreamSynchronize(st));
+  std::memcpy(torque, h->hTq, N * nu * B);
+  return OSC_OK;
+}
+
 int osc_step_host(osc_handle* h, const double* M, const double* C, const double* J,
                   const double* bias, const double* targets, const double* mask, double* torque,
                   void* stream) {
@@ -1100,6 +1170,7 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
   }
   cudaStream_t st = (cudaStream_t)stream;
   OSC_CUDA(h, cudaSetDevice(h->device));
+  if (h->in_doubles * sizeof(double) <= kFewRobotsBytes) return step_host_few(h, M, C, J, bias, targets, mask, torque, st);
   // Software pipeline over chunks of environments: the H2D copy of chunk c+1 (copy stream)
   // overlaps build+solve of chunk c (caller's stream); torques return per chunk.
   const int N = h->n_envs;
