@@ -16,6 +16,7 @@
 //                     copies overlap the solve of the current one): assembly, factorisation,
 //                     ADMM with register-resident matrices, un-scaling, entirely on chip in
 //                     FP64 (osc::Core3::step_prepare / step_solve).
+//   order_kernel      longest-first hand-out order of solve_kernel3's work counter (scheduling).
 //   reset_warm_kernel reset_optimization().
 //   targets_pd_kernel, contact_mask_kernel
 //                     the step before the path for device-resident roll-outs: task-space PD
@@ -322,6 +323,9 @@ struct SolveArgs {
   // launch's tickets start (`base`) without a memset between the kernels
   unsigned* counter;
   unsigned base;
+  // ticket -> environment (a permutation of [0, n_envs), longest expected solves first), or
+  // NULL for the identity
+  const int* order;
   int* reinits;
   int n_envs;
 };
@@ -420,7 +424,9 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   // round trip of the atomic overlaps step_prepare) and later starts landing it (`land`:
   // eight bulk copies into the stage; returns the index to all lanes)
   auto draw = [&]() -> int {
-    return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0;
+    if (lane != 0) return 0;
+    const int t = (int)(atomicAdd(a.counter, 1u) - a.base);
+    return (a.order && t < a.n_envs) ? a.order[t] : t;
   };
   auto land = [&](int env) -> int {
     if (lane == 0 && env < a.n_envs) {
@@ -469,6 +475,39 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     OSC_TICK(8);
     env = next;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Longest-processing-time-first order for solve_kernel3's work counter.  The kernel's
+// duration is bounded below by its slowest environment; iteration counts of warm-started
+// control steps are persistent (the ill-conditioned environments stay so), so every few
+// steps the environments are bucketed by their last iteration count (counting sort, one
+// CTA) and the solve kernel hands out the expensive ones first instead of meeting one of
+// them in its last wave.
+// ---------------------------------------------------------------------------
+constexpr int kOrderBuckets = 64;
+__global__ void __launch_bounds__(1024) order_kernel(const int* __restrict__ iters, int n,
+                                                     int* __restrict__ order) {
+  __shared__ int cursor[kOrderBuckets];
+  auto bucket = [](int it) {
+    const int b = it >> 3;
+    return b < kOrderBuckets ? b : kOrderBuckets - 1;
+  };
+  if (threadIdx.x < kOrderBuckets) cursor[threadIdx.x] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < n; e += blockDim.x) atomicAdd(&cursor[bucket(iters[e])], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // first slot of every bucket, largest iteration counts first
+    int at = 0;
+    for (int b = kOrderBuckets - 1; b >= 0; --b) {
+      const int c = cursor[b];
+      cursor[b] = at;
+      at += c;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n; e += blockDim.x)
+    order[atomicAdd(&cursor[bucket(iters[e])], 1)] = e;
 }
 
 // ---------------------------------------------------------------------------
@@ -615,6 +654,9 @@ struct osc_handle {
   double *dTorque, *dX, *dY, *dPri, *dDua, *dRho;
   int *dIters, *dStatus, *dCounter;
   std::vector<unsigned> ctr_base;  // first ticket of the next launch on every work counter
+  int* dOrder;      // solve order of the resident full-batch step (order_kernel)
+  int order_age;    // osc_step calls since it was rebuilt
+  bool use_order;   // set by osc_step around its full-batch solve launch
   // inputs actually read by the kernels (own buffers unless osc_bind_device_inputs)
   const double *iM, *iC, *iJ, *iBias, *iTargets, *iMask;
   // pipelined host path: copy stream + per-chunk events and work counters
@@ -758,6 +800,7 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   a.iters = h->dIters + e; a.status = h->dStatus + e;
   a.counter = reinterpret_cast<unsigned*>(h->dCounter) + counter;
   a.base = h->ctr_base[counter];
+  a.order = (h->use_order && env0 == 0 && n == h->n_envs) ? h->dOrder : nullptr;
   a.reinits = h->dCounter + h->n_counters;
   a.scal = h->dScal + e * osc::Core3<D>::SCAL;
   a.n_envs = n;
@@ -890,6 +933,9 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   if ((ce = cudaEventCreateWithFlags(&h->fence_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
   cudaMemset(h->dCounter, 0, (2 * h->n_counters + 1) * sizeof(int));
   h->ctr_base.assign(2 * h->n_counters + 1, 0u);
+  if ((ce = cudaMalloc((void**)&h->dOrder, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  h->order_age = -1;  // no order yet
+  h->use_order = false;
   cudaMemset(h->dIters, 0, N * sizeof(int));
   cudaMemset(h->dStatus, 0, N * sizeof(int));
   h->iM = h->dM; h->iC = h->dC; h->iJ = h->dJ; h->iBias = h->dBias; h->iTargets = h->dTargets;
@@ -927,6 +973,7 @@ int osc_destroy(osc_handle* h) {
   if (h->dIters) cudaFree(h->dIters);
   if (h->dStatus) cudaFree(h->dStatus);
   if (h->dCounter) cudaFree(h->dCounter);
+  if (h->dOrder) cudaFree(h->dOrder);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
   if (h->fence_ev) cudaEventDestroy(h->fence_ev);
@@ -974,6 +1021,8 @@ int osc_setup(osc_handle* h, void* stream) {
   return OSC_OK;
 }
 
+constexpr int kOrderEvery = 8;
+
 int osc_step(osc_handle* h, void* stream) {
   if (check_handle(h)) return OSC_ERR_INVALID;
   if (!h->setup_done) {
@@ -982,6 +1031,15 @@ int osc_step(osc_handle* h, void* stream) {
   }
   cudaStream_t st = (cudaStream_t)stream;
   OSC_CUDA(h, cudaSetDevice(h->device));
+  // solve order: rebuilt from the last iteration counts every kOrderEvery steps (batches of
+  // more than one wave only; a smaller batch has every environment in flight at once)
+  const bool ordered = h->n_envs > h->sm_count * 8;
+  if (ordered && (h->order_age < 0 || h->order_age >= kOrderEvery)) {
+    osc::order_kernel<<<1, 1024, 0, st>>>(h->dIters, h->n_envs, h->dOrder);
+    OSC_CUDA(h, cudaGetLastError());
+    h->launches++;
+    h->order_age = 0;
+  }
   cudaEvent_t* ev = nullptr;
   if (h->timing) {
     if (h->ev_used + 4 > h->ev.size()) {
@@ -1000,9 +1058,12 @@ int osc_step(osc_handle* h, void* stream) {
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
   // ev[2] = scale | solve boundary: recorded by launch_solve3 between its two kernels
   h->timing_mid = ev ? ev[2] : nullptr;
+  h->use_order = ordered;
   rc = OSC_DISPATCH(h, launch_solve, h, st, 0, h->n_envs, 0);
+  h->use_order = false;
   h->timing_mid = nullptr;
   if (rc) return rc;
+  if (ordered) h->order_age++;
   h->kernels_ready = true;  // function attributes / occupancy are set from here on
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[3], st));
   return OSC_OK;
