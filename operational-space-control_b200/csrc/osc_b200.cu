@@ -489,13 +489,27 @@ constexpr int kOrderBuckets = 64;
 __global__ void __launch_bounds__(1024) order_kernel(const int* __restrict__ iters, int n,
                                                      int* __restrict__ order) {
   __shared__ int cursor[kOrderBuckets];
-  auto bucket = [](int it) {
-    const int b = it >> 3;
-    return b < kOrderBuckets ? b : kOrderBuckets - 1;
+  const int lane = threadIdx.x & 31;
+  // most environments share one bucket: the lanes of a warp that do are counted / placed with
+  // ONE shared-memory atomic (match.any), not one each on the same word
+  auto claim = [&](int e) -> int {
+    const bool valid = e < n;
+    int b = -1;
+    if (valid) {
+      b = iters[e] >> 3;
+      b = b < kOrderBuckets ? b : kOrderBuckets - 1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (valid && lane == leader) base = atomicAdd(&cursor[b], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return valid ? base + __popc(peers & ((1u << lane) - 1u)) : -1;
   };
   if (threadIdx.x < kOrderBuckets) cursor[threadIdx.x] = 0;
   __syncthreads();
-  for (int e = threadIdx.x; e < n; e += blockDim.x) atomicAdd(&cursor[bucket(iters[e])], 1);
+  const int rounds = (n + blockDim.x - 1) / blockDim.x;  // same trip count for every thread
+  for (int r = 0; r < rounds; ++r) claim(r * blockDim.x + threadIdx.x);
   __syncthreads();
   if (threadIdx.x == 0) {  // first slot of every bucket, largest iteration counts first
     int at = 0;
@@ -506,8 +520,11 @@ __global__ void __launch_bounds__(1024) order_kernel(const int* __restrict__ ite
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < n; e += blockDim.x)
-    order[atomicAdd(&cursor[bucket(iters[e])], 1)] = e;
+  for (int r = 0; r < rounds; ++r) {
+    const int e = r * blockDim.x + threadIdx.x;
+    const int pos = claim(e);
+    if (pos >= 0) order[pos] = e;
+  }
 }
 
 // ---------------------------------------------------------------------------
