@@ -122,7 +122,9 @@ const char *osc_last_error(const osc_handle *h);
 int osc_num_envs(const osc_handle *h);
 int osc_get_device_buffers(osc_handle *h, osc_device_buffers *out);
 
-/* Host AoS -> device (pinned staging + cudaMemcpyAsync on `stream`).  Replaces the
+/* Host AoS -> device: cudaMemcpyAsync on `stream` straight from the caller's arrays (no
+ * staging copy).  The copies run at full PCIe rate and asynchronously only from page-locked
+ * memory (osc_host_alloc); from pageable memory every copy blocks the host.  Replaces the
  * six row->column-major copies of update_optimization_data (:517-522): no
  * transposes are needed, the kernels read the reference's row-major layout.
  * Any pointer may be NULL to leave that field unchanged. `stream` is a cudaStream_t. */
@@ -160,7 +162,11 @@ int osc_download_objective(osc_handle *h, double *H_dv, double *f_dv, void *stre
  * contact_jacobian is the contact rows only).  Everything else goes up in full.
  * A handle of a few robots (inputs <= 128 KiB: the reference's own one-robot 1 kHz loop) takes a
  * low-latency route instead: the inputs are staged in one pinned slab, uploaded with a single
- * copy on `stream`, and the torques return through pinned memory. */
+ * copy on `stream`, and the torques return through pinned memory.
+ * The chunked pipeline copies straight from / to the caller's buffers: the overlap of the H2D
+ * copy of chunk c+1 with the kernels of chunk c needs PAGE-LOCKED host buffers (osc_host_alloc);
+ * with pageable memory the call is still correct but every copy blocks.  Fails with
+ * OSC_ERR_STATE while any input is bound to caller-owned device memory. */
 int osc_step_host(osc_handle *h, const double *M, const double *C, const double *J,
                   const double *bias, const double *targets, const double *mask, double *torque,
                   void *stream);

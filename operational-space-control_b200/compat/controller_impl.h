@@ -183,6 +183,12 @@ class Controller {
     return step_locked();
   }
   void set_device(int d) { device = d; }
+  // B200 build only: control steps completed so far (synchronous + control_loop), so that a
+  // test can tell which step a published torque belongs to.
+  long long steps_done() {
+    std::lock_guard<std::mutex> lock(mutex);
+    return steps;
+  }
 
  private:
   absl::Status upload() {
@@ -207,6 +213,7 @@ class Controller {
                      nullptr, nullptr, nullptr) != OSC_OK ||
         osc_sync(handle, nullptr) != OSC_OK)
       return absl::InternalError(std::string("osc_download: ") + osc_last_error(handle));
+    ++steps;
     return absl::OkStatus();
   }
   void control_loop() {
@@ -241,6 +248,7 @@ class Controller {
   int control_rate_us;
   osqp::OsqpSettings settings;
   int exit_code = OSC_UNSOLVED;
+  long long steps = 0;
   int device = 0;
   osc_handle* handle = nullptr;
   std::atomic<bool> running{true};

@@ -146,6 +146,9 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
   constexpr uint32_t kBytes = sizeof(BuildStage<D>);
   auto issue = [&](int stage, int env) {
     BuildStage<D>& st = my[stage];
+    // the stage was read and (bias -> r, in place) written through the generic proxy: order
+    // those accesses before the async-proxy writes of the bulk copies
+    fence_proxy_async();
     mbar_expect_tx(&mybar[stage], kBytes);
     bulk_g2s(st.J, J + (size_t)env * S * NV, sizeof(st.J), &mybar[stage]);
     bulk_g2s(st.bias, bias + (size_t)env * S, sizeof(st.bias), &mybar[stage]);
@@ -874,8 +877,11 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   if (settings) st = *settings; else osc::default_settings(&st);
   if (st.max_iter < 1 || st.check_termination < 0 || st.scaling < 0 || st.rho <= 0 ||
       st.sigma <= 0 || st.alpha <= 0 || st.alpha >= 2 || st.eps_prim_inf <= 0 ||
-      st.eps_dual_inf <= 0) {
-    g_create_err = "osc_create: invalid settings";
+      st.eps_dual_inf <= 0 || st.eps_abs < 0 || st.eps_rel < 0 ||
+      (st.adaptive_rho && st.adaptive_rho_tolerance < 1.0) || st.adaptive_rho_interval < 0) {
+    // the ranges of OSQP 0.6.3 validate_settings (auxil.c) for the fields osc_settings carries;
+    // eps_abs == eps_rel == 0 stays legal here: it is the fixed-iteration-budget mode
+    g_create_err = "osc_create: invalid settings (OSQP validate_settings ranges)";
     return OSC_ERR_INVALID;
   }
   int count = 0;
@@ -910,8 +916,11 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail(ce, "cudaSetDevice");
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(ce, "cudaGetDeviceProperties");
-  if (prop.major < 10) {
-    g_create_err = "osc_create: kernels are built for sm_100a only";
+  if (prop.major != 10 || prop.minor != 0) {
+    // architecture-specific SASS (sm_100a) has no forward compatibility: CC 10.3 / 12.x devices
+    // would fail later with "no kernel image"
+    g_create_err = "osc_create: kernels are built for sm_100a (compute capability 10.0) only; device is " +
+                   std::to_string(prop.major) + "." + std::to_string(prop.minor);
     osc_destroy(h);
     return OSC_ERR_CUDA;
   }
@@ -1205,8 +1214,8 @@ static int step_host_few(osc_handle* h, const double* M, const double* C, const 
   if (!h->hIn) {
     OSC_CUDA(h, cudaHostAlloc((void**)&h->hIn, h->in_doubles * B, cudaHostAllocDefault));
     std::memset(h->hIn, 0, h->in_doubles * B);
-    OSC_CUDA(h, cudaHostAlloc((void**)&h->hTq, N * nu * B, cudaHostAllocDefault));
   }
+  if (!h->hTq) OSC_CUDA(h, cudaHostAlloc((void**)&h->hTq, N * nu * B, cudaHostAllocDefault));
   std::memcpy(h->hIn + h->in_off[0], M, N * nv * nv * B);
   std::memcpy(h->hIn + h->in_off[1], C, N * nv * B);
   for (size_t e = 0; e < N; ++e)  // only the rows the kernels read leave the caller's buffer
@@ -1242,7 +1251,8 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
     h->err = "osc_step_host: null host buffer";
     return OSC_ERR_INVALID;
   }
-  if (h->iM != h->dM || h->iJ != h->dJ) {
+  if (h->iM != h->dM || h->iC != h->dC || h->iJ != h->dJ || h->iBias != h->dBias ||
+      h->iTargets != h->dTargets || h->iMask != h->dMask) {
     h->err = "osc_step_host: inputs are bound to caller-owned device memory (osc_bind_device_inputs)";
     return OSC_ERR_STATE;
   }

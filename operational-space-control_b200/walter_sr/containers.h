@@ -1,7 +1,8 @@
 #pragma once
 // Same records as the reference's walter_sr/containers.h:13-42.  OSCData is the GPU-boundary
-// input record; OptimizationData never exists on the host in this build (H, f, Aeq, ... are
-// formed on the device).
+// input record; OptimizationData is kept for callers that name it (:23-31) but is never
+// filled on the host in this build: H, f, Aeq, ... are formed on the device
+// (osc_download_objective returns the dv block of H and f for inspection).
 #include "operational-space-control/walter_sr/aliases.h"
 
 namespace operational_space_controller {
@@ -16,6 +17,15 @@ namespace operational_space_controller {
             Vector<optimization::s_size> taskspace_bias;
             Vector<model::nq_size> previous_q;
             Vector<model::nv_size> previous_qd;
+        };
+
+        struct OptimizationData {
+            MatrixColMajor<optimization::H_rows, optimization::H_cols> H;
+            Vector<optimization::f_sz> f;
+            MatrixColMajor<optimization::Aeq_rows, optimization::Aeq_cols> Aeq;
+            Vector<optimization::beq_sz> beq;
+            Matrix<optimization::Aineq_rows, optimization::Aineq_cols> Aineq;
+            Vector<optimization::bineq_sz> bineq;
         };
 
         struct State {

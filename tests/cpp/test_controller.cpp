@@ -6,8 +6,10 @@
 #include <cstdlib>
 #include <vector>
 
-#ifdef ROBOT_GO2
+#if defined(ROBOT_GO2)
 #include "operational-space-control/unitree_go2/operational_space_controller.h"
+#elif defined(ROBOT_WW)
+#include "operational-space-control/walter_sr_wheels/operational_space_controller.h"
 #else
 #include "operational-space-control/walter_sr/operational_space_controller.h"
 #endif
@@ -64,9 +66,16 @@ int main(int argc, char** argv) {
   result = controller.stop_thread();
   if (!result.ok()) return 1;
   auto torque2 = controller.get_torque_command();
+  // the thread ran steps_done() - 1 warm control steps on the same inputs after the
+  // synchronous one: the test replays exactly that many on the oracle
+  std::printf("THREAD_STEPS %lld\n", controller.steps_done());
   std::printf("TORQUE_THREAD");
   for (int i = 0; i < model::nu_size; ++i) std::printf(" %.17g", torque2(i));
   std::printf("\n");
+  {  // a caller that names the reference's OptimizationData record still compiles (:23-31)
+    OptimizationData od;
+    std::printf("OPTDATA %d %d\n", (int)od.H.size(), (int)od.Aineq.size());
+  }
   result = controller.clean_up();
   if (!result.ok()) return 1;
   // the N-environment sibling: three copies of the same robot, host step then resident step

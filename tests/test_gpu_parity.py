@@ -207,23 +207,34 @@ def test_gpu_matches_committed_golden_fixture():
             assert (d <= tol).all(), (key, (d / tol).max())
 
 
+ROBOT_BUILDS = (("", "walter_sr", "standing"), ("-DROBOT_GO2", "unitree_go2", "go2_standing"),
+                ("-DROBOT_WW", "walter_sr_wheels", "stairs"))
+
+
+def _build_cpp(tmp_path, source, macro, name, extra=()):
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / name
+    pkg = os.path.join(ROOT, "operational-space-control_b200")
+    cmd = ["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "include"), *extra,
+           os.path.join(ROOT, "tests", "cpp", source), "-o", str(exe),
+           "-L", pkg, "-losc_b200", f"-Wl,-rpath,{pkg}", "-lpthread"]
+    if macro:
+        cmd.insert(1, macro)
+    subprocess.run(cmd, check=True)
+    return exe
+
+
 def test_cpp_controller_class_drop_in(oracle, tmp_path):
     """The reference-named C++ class (OperationalSpaceController) over the C-ABI, driven like
-    examples/walter_sr_standing.cc:89-167 with OSCData injected; torques vs the oracle."""
+    examples/walter_sr_standing.cc:89-167 with OSCData injected; torques vs the oracle.  All
+    three robot headers (walter_sr, unitree_go2, walter_sr_wheels)."""
     import subprocess
     import osc_b200 as ob
-    from conftest import ROOT
-    for macro, preset, config in (("", "walter_sr", "standing"), ("-DROBOT_GO2", "unitree_go2", "go2_standing")):
+    for macro, preset, config in ROBOT_BUILDS:
         spec = ob.load_preset(preset)
         inp = ob.synth.make_inputs(spec, 1, config)
-        exe = tmp_path / f"test_controller_{preset}"
-        pkg = os.path.join(ROOT, "operational-space-control_b200")
-        cmd = ["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "include"),
-               os.path.join(ROOT, "tests", "cpp", "test_controller.cpp"), "-o", str(exe),
-               "-L", pkg, "-losc_b200", f"-Wl,-rpath,{pkg}", "-lpthread"]
-        if macro:
-            cmd.insert(1, macro)
-        subprocess.run(cmd, check=True)
+        exe = _build_cpp(tmp_path, "test_controller.cpp", macro, f"test_controller_{preset}")
         blob = tmp_path / f"{preset}.bin"
         with open(blob, "wb") as fh:
             for k in ("M", "C", "J", "bias", "targets", "mask"):
@@ -231,21 +242,69 @@ def test_cpp_controller_class_drop_in(oracle, tmp_path):
         out = subprocess.run([str(exe), str(blob)], check=True, capture_output=True, text=True).stdout
         lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l.strip()}
         assert lines["SLICE_OK"] == ["1"], out
+        assert lines["OPTDATA"] == [str(spec.n * spec.n), str(4 * spec.nc * spec.n)], out
         tq = np.array([float(v) for v in lines["TORQUE"]])
         b = oracle.OracleBatch(spec, 1, oracle.default_settings())
         b.setup(inp)
         o = b.step(inp)
         tol = ATOL + RTOL * np.abs(o["torque"][0])
         assert (np.abs(tq - o["torque"][0]) <= tol).all(), (preset, tq, o["torque"][0])
+        # control_loop on its own thread: the published torque is the one of warm step number
+        # THREAD_STEPS on the same inputs -- replay exactly that many on the oracle
+        n_steps = int(lines["THREAD_STEPS"][0])
+        assert n_steps >= 3, out  # 40 ms of a 2 ms loop (a loaded box may skip periods)
+        ot = o
+        for _ in range(n_steps - 1):
+            ot = b.step(inp)
         tq2 = np.array([float(v) for v in lines["TORQUE_THREAD"]])
-        assert np.isfinite(tq2).all() and np.abs(tq2 - tq).max() < 1.0 + 0.1 * np.abs(tq).max()
+        tol_t = ATOL + RTOL * np.abs(ot["torque"][0])
+        assert (np.abs(tq2 - ot["torque"][0]) <= tol_t).all(), (preset, n_steps, tq2, ot["torque"][0])
         # BatchedOperationalSpaceController: same first step bit for bit, then a warm resident step
         tb = np.array([float(v) for v in lines["TORQUE_BATCH"]])
         assert np.array_equal(tb, tq), (preset, tb, tq)
-        o2 = b.step(inp)
+        b2 = oracle.OracleBatch(spec, 1, oracle.default_settings())
+        b2.setup(inp)
+        b2.step(inp)
+        o2 = b2.step(inp)
         tr = np.array([float(v) for v in lines["TORQUE_RESIDENT"]])
         tol2 = ATOL + RTOL * np.abs(o2["torque"][0])
         assert (np.abs(tr - o2["torque"][0]) <= tol2).all(), (preset, tr, o2["torque"][0])
+
+
+def test_cpp_controller_mujoco_branch_on_fake_backend(oracle, tmp_path):
+    """update_mj_data / update_osc_data of the drop-in classes (reference :394-513), compiled
+    against tests/stubs/mujoco/mujoco.h and run on the scripted backend tests/stubs/fake_mujoco.cc:
+    M, C, J, bias reach the device through mj_fullM / qfrc_bias / mj_jac / mj_jacDot, nothing is
+    injected; torques vs the oracle on the same numbers, and the qpos / qvel packing (:402-404)."""
+    import subprocess
+    import osc_b200 as ob
+    from conftest import ROOT
+    stubs = os.path.join(ROOT, "tests", "stubs")
+    for macro, preset, config in ROBOT_BUILDS:
+        spec = ob.load_preset(preset)
+        inp = ob.synth.make_inputs(spec, 1, config)
+        exe = _build_cpp(tmp_path, "test_controller_mujoco.cpp", macro, f"test_mj_{preset}",
+                         extra=["-I", stubs, os.path.join(stubs, "fake_mujoco.cc")])
+        model = tmp_path / f"{preset}_model.bin"
+        with open(model, "wb") as fh:
+            fh.write(np.array([spec.nv, spec.nu, spec.ns, spec.nc], np.int32).tobytes())
+            for k in ("M", "C", "J", "bias"):
+                fh.write(np.ascontiguousarray(inp[k][0]).tobytes())
+        tm = tmp_path / f"{preset}_targets.bin"
+        with open(tm, "wb") as fh:
+            for k in ("targets", "mask"):
+                fh.write(np.ascontiguousarray(inp[k][0]).tobytes())
+        out = subprocess.run([str(exe), str(model), str(tm)], check=True, capture_output=True,
+                             text=True).stdout
+        lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l.strip()}
+        assert lines["QPOS_OK"] == ["1"], out
+        assert int(lines["FORWARD_CALLS"][0]) == 2, out  # set_up_optimization + one control step
+        tq = np.array([float(v) for v in lines["TORQUE"]])
+        b = oracle.OracleBatch(spec, 1, oracle.default_settings())
+        b.setup(inp)
+        o = b.step(inp)
+        tol = ATOL + RTOL * np.abs(o["torque"][0])
+        assert (np.abs(tq - o["torque"][0]) <= tol).all(), (preset, tq, o["torque"][0])
 
 
 @pytest.mark.parametrize("preset,config", [("walter_sr_true_tumbling_mjjoint", "tumbling"),
