@@ -31,8 +31,19 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "operational-space-control_b200", "python"))
-# stdout carries exactly one JSON line: keep NCCL's version banner off it
-os.environ["NCCL_DEBUG"] = os.environ.get("OSC_BENCH_NCCL_DEBUG", "WARN")
+# stdout carries exactly one JSON line.  NCCL (and anything else in native code) prints to
+# fd 1, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate
+# of the original stdout: NCCL's INFO lines (rank counts, NVLS / P2P transports) stay visible
+# on stderr instead of being silenced.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+os.environ.setdefault("NCCL_DEBUG", "INFO")
+os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -55,16 +66,19 @@ METRIC = "OSC solves/sec (whole box)"
 UNIT = "solves/s"
 
 
-def algorithmic_flops_per_solve(spec, k_mean):
+def algorithmic_flops_per_solve(spec, iters, check_every=25):
     """dense-reduced-form operation count of the solver part (the H/f build
     is the other kernel): reduced system + Cholesky once, per-iteration solve + products,
-    per-check residuals every 25 iterations."""
+    per-check residuals every 25 iterations.  `iters` = per-environment iteration counts:
+    the number of residual checks is the mean of ceil(k / 25) per environment (not ceil of
+    the mean, which counted two checks per solve for a mean of 25.1)."""
     n, nv, nc = spec.n, spec.nv, spec.nc
+    iters = np.asarray(iters, dtype=np.float64)
     setup = nv * n * n + n ** 3 / 3.0
     nnzA = nv * n + 12 * nc + n
     per_iter = 2 * 2 * nnzA + 2 * n * n + 12 * spec.m
     per_check = 2 * n * n + 2 * nnzA
-    return setup + per_iter * k_mean + per_check * np.ceil(k_mean / 25.0)
+    return float(setup + per_iter * iters.mean() + per_check * np.ceil(iters / check_every).mean())
 
 
 def scale_ops_per_solve(spec, passes=10):
@@ -135,6 +149,148 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa(local):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its
+    GPU hangs off, so that the H2D stream does not cross the socket interconnect.  Returns
+    (info dict, original affinity) -- the affinity is restored before the CPU baseline runs."""
+    orig = None
+    info = {"node": None, "cpus": None}
+    try:
+        orig = os.sched_getaffinity(0)
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader",
+                              "-i", str(local)], capture_output=True, text=True, timeout=20).stdout
+        bus = out.strip().splitlines()[0].strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= orig
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info = {"node": node, "cpus": len(cpus)}
+    except Exception as e:  # no sysfs / nvidia-smi: keep the default placement
+        info["error"] = type(e).__name__
+    return info, orig
+
+
+def device_peak_dfma(capi, local, cache={}):
+    if local not in cache:
+        cache[local] = capi.measure_dfma_tflops(local)
+    return cache[local]
+
+
+def measure_resident(ob, capi, sharding, torch, spec, wl, n_envs, steps, warmup, nsets, rank,
+                     world, local, dev, hbm_peak, with_dual=False):
+    """Device-resident warm-step throughput of one (robot, config, batch size) point: the same
+    protocol as the headline (inputs in HBM, `nsets` resident control ticks cycling, CUDA
+    events on the launch stream, max over ranks), plus the per-kernel roofline fractions."""
+    stream = torch.cuda.current_stream().cuda_stream
+    dev_sets = []
+    for t in range(nsets):
+        inp = ob.synth.make_inputs(spec, n_envs, wl["config"], first_env=rank * n_envs, step=t)
+        dev_sets.append({k: torch.from_numpy(inp[k]).to(dev) for k in FIELDS})
+        del inp
+    in_bytes = sum(v.numel() * 8 for v in dev_sets[0].values())
+    osc = capi.BatchedOSC(spec, n_envs, device=local)
+
+    def bind(t):
+        d = dev_sets[t % nsets]
+        osc.bind_device_inputs(*[d[k].data_ptr() for k in FIELDS])
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    bind(0)
+    osc.setup(stream=stream)
+    for t in range(warmup):
+        bind(t)
+        osc.step_device(stream)
+    osc.enable_timing(True)
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i, t in enumerate(range(warmup, warmup + steps)):
+        bind(t)
+        osc.step_device(stream)
+        evs[i + 1].record()
+    barrier()
+    ms = sharding.max_over_ranks(evs[0].elapsed_time(evs[-1]), dev) / steps
+    p50 = sharding.max_over_ranks(
+        float(np.median([a.elapsed_time(b) for a, b in zip(evs, evs[1:])])), dev)
+    kt = osc.read_timing()
+    osc.enable_timing(False)
+    res = osc.results(stream)
+    dfma = device_peak_dfma(capi, local)
+    flops = algorithmic_flops_per_solve(spec, res["iters"]) * n_envs
+    out = {"robot": spec.robot, "preset": wl["preset"], "synthetic_config": wl["config"],
+           "envs_per_gpu": n_envs, "total_envs": world * n_envs, "steps": steps,
+           "value": world * n_envs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+           "p50_batch_latency_ms": p50, "iters_mean": float(res["iters"].mean()),
+           "solved_frac": float((res["status"] == capi.SOLVED).mean()),
+           "inputs_exceed_l2": bool(nsets * in_bytes > 126e6),
+           "kernel_ms": {"build_qp_kernel": kt.build_ms, "scale_kernel3": kt.scale_ms,
+                         "solve_kernel3": kt.solve_ms},
+           "roofline": {"kernel": "solve_kernel3", "bound": "fp64_fma",
+                        "achieved": flops / (kt.solve_ms * 1e-3) / 1e12, "peak": dfma,
+                        "unit": "TFLOP/s",
+                        "frac": flops / (kt.solve_ms * 1e-3) / 1e12 / dfma},
+           "roofline_scale_frac": scale_ops_per_solve(spec, 10) * n_envs
+                                  / (kt.scale_ms * 1e-3) / 1e12 / (dfma / 2.0),
+           "roofline_build_frac": build_bytes_per_solve(spec) * n_envs
+                                  / (kt.build_ms * 1e-3) / 1e9 / hbm_peak}
+    if with_dual:
+        # contacts whose friction pyramid is active at the solution: a friction row with a
+        # positive multiplier (rows nv .. nv + 4 nc of the dual) on an unmasked contact
+        yf = res["y"][:, spec.nv:spec.nv + 4 * spec.nc].reshape(n_envs, spec.nc, 4)
+        mk = dev_sets[(warmup + steps - 1) % nsets]["mask"].cpu().numpy() > 0
+        act = (yf > 1e-6).any(2) & mk
+        out["friction_cone_active_frac_envs"] = float(act.any(1).mean())
+        out["friction_cone_active_frac_contacts"] = float(act.sum() / max(1, mk.sum()))
+    osc.close()
+    del dev_sets
+    torch.cuda.empty_cache()
+    return out
+
+
+def one_robot_latency(ob, capi, spec, wl, local, reps=300):
+    """BASELINE configs[0]: ONE Walter Sr in the reference's own loop -- host buffers in,
+    torque out per control step (osc_step_host on a one-environment handle), wall clock."""
+    steps = [ob.synth.make_inputs(spec, 1, wl["config"], step=t) for t in range(NSETS)]
+    osc = capi.BatchedOSC(spec, 1, device=local)
+    osc.setup(steps[0])
+    tq = capi.pinned_empty((1, spec.nu))
+    pin = []
+    for st in steps:
+        d = {}
+        for k in FIELDS:
+            a = capi.pinned_empty(st[k].shape)
+            a[...] = st[k]
+            d[k] = a
+        pin.append(d)
+    ptrs = [[d[k].ctypes.data for k in FIELDS] for d in pin]
+    for t in range(20):
+        osc.step_host_into(ptrs[t % NSETS], tq)
+    lat = []
+    for t in range(reps):
+        t0 = time.perf_counter()
+        osc.step_host_into(ptrs[t % NSETS], tq)
+        lat.append(time.perf_counter() - t0)
+    r = osc.results()
+    osc.close()
+    lat = np.array(lat) * 1e6
+    return {"robot": spec.robot, "preset": wl["preset"], "envs": 1, "reps": reps,
+            "p50_step_latency_us": float(np.median(lat)), "p99_step_latency_us": float(np.percentile(lat, 99)),
+            "value": 1e6 / float(np.median(lat)), "unit": UNIT,
+            "iters": int(r["iters"][0]), "note": "wall clock per control step: pinned host buffers "
+            "in, 3 kernels, torque back to the host (osc_step_host, few-robot path)"}
+
+
 def cpu_leg(spec, wl, sample_envs, steps, warmup, n_threads=0):
     """The reference's CPU path (oracle port), all host threads, same warm-step protocol on
     a bounded sample of the workload.  Returns (solves/s, info dict)."""
@@ -187,7 +343,7 @@ def run_reference(args, wl, spec):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -199,6 +355,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the other BASELINE configs / sweep points (headline only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -221,6 +379,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa, orig_affinity = bind_to_gpu_numa(local)  # before the pinned buffers are touched
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -314,25 +473,110 @@ def main():
         osc.step_host_into(ptrs[t % NSETS], tq, stream)
     g1.record()
     barrier()
-    e2e_ms = sharding.max_over_ranks(g0.elapsed_time(g1), dev) / args.steps
+    e2e_ms_local = g0.elapsed_time(g1) / args.steps
+    e2e_ms = sharding.max_over_ranks(e2e_ms_local, dev) / 1.0
     e2e_wall_ms = sharding.max_over_ranks(1e3 * (time.perf_counter() - w0), dev) / args.steps
     e2e_value = world * n_envs / (e2e_ms * 1e-3)
     # bytes the C-ABI actually moved per step (it skips Jacobian rows nothing reads)
     e2e_h2d, e2e_d2h = osc.host_traffic()
 
-    # ---- off the hot path: one all-gather of torques + statistics
-    gather_ms = None
+    # ---- the all-gather of torques + statistics as peer stores behind the
+    #      C-ABI (osc_gather_*): timed alone, and inside a second timed loop of resident
+    #      steps so that `value_incl_gather` is measured, not derived
+    sharding.setup_peer_gather(osc, rank, world, dev)
+    osc.bind_device_inputs(*[dev_sets[0][k].data_ptr() for k in FIELDS])
+    osc.setup(stream=stream)
+    for t in range(args.warmup):
+        bind(t)
+        osc.step_device(stream)
+        osc.gather_torques(stream)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for t in range(args.warmup, args.warmup + args.steps):
+        bind(t)
+        osc.step_device(stream)
+        osc.gather_torques(stream)
+    h1.record()
+    barrier()
+    ms_incl = sharding.max_over_ranks(h0.elapsed_time(h1), dev) / args.steps
+    value_incl_gather = world * n_envs / (ms_incl * 1e-3)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(20):
+        osc.gather_torques(stream)
+    a1.record()
+    barrier()
+    gather_ms = sharding.max_over_ranks(a0.elapsed_time(a1), dev) / 20
+    # cross-check of the peer-store path: every rank's gathered copy == an NCCL all-gather
+    t_ptr, s_ptr = osc.gather_buffers()
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    got = torch.empty((world * n_envs, spec.nu), dtype=torch.float64, device=dev)
+    rt.cudaMemcpy(ctypes.c_void_p(got.data_ptr()), ctypes.c_void_p(t_ptr),
+                  ctypes.c_size_t(got.numel() * 8), 3)
+    gstats = torch.empty((world, capi.GATHER_STATS), dtype=torch.float64, device=dev)
+    rt.cudaMemcpy(ctypes.c_void_p(gstats.data_ptr()), ctypes.c_void_p(s_ptr),
+                  ctypes.c_size_t(gstats.numel() * 8), 3)
+    mine = torch.from_numpy(osc.torques(stream)).to(dev)
+    gather_check, nccl_gather_ms = True, None
     if world > 1:
-        tq_dev = torch.from_numpy(np.ascontiguousarray(tq)).to(dev)
-        sharding.all_gather_rows(tq_dev, world * n_envs, world)  # NCCL lazy init, untimed
+        ref = torch.empty_like(got)
+        dist.all_gather_into_tensor(ref, mine)  # NCCL lazy init, untimed
         barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        allt = sharding.all_gather_rows(tq_dev, world * n_envs, world)
-        a1.record()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        dist.all_gather_into_tensor(ref, mine)
+        n1.record()
         barrier()
-        assert allt.shape[0] == world * n_envs
-        gather_ms = sharding.max_over_ranks(a0.elapsed_time(a1), dev)
+        nccl_gather_ms = sharding.max_over_ranks(n0.elapsed_time(n1), dev)
+        ok = torch.equal(ref, got)
+        gather_check = bool(sharding.max_over_ranks(0.0 if ok else 1.0, dev) == 0.0)
+    else:
+        gather_check = bool(torch.equal(got, mine))
+    gstats = gstats.cpu().numpy()
+    # per-rank PCIe rate of the end-to-end leg (shows switch / socket sharing at N > 1)
+    my_gbs = e2e_h2d / (e2e_ms_local * 1e-3) / 1e9
+    if world > 1:
+        allg = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allg, torch.tensor([my_gbs], dtype=torch.float64, device=dev))
+        pcie_per_rank = [float(x.item()) for x in allg]
+        alln = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(alln, torch.tensor([float(numa["node"] if numa["node"] is not None else -1)],
+                                           dtype=torch.float64, device=dev))
+        numa_per_rank = [int(x.item()) for x in alln]
+    else:
+        pcie_per_rank = [my_gbs]
+        numa_per_rank = [numa["node"] if numa["node"] is not None else -1]
+
+    # ---- the other BASELINE configs and the per-GPU sweep points, same protocol (few steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    configs = None
+    if not args.no_configs and args.workload == DEFAULT_WORKLOAD and not args.envs_per_gpu:
+        osc.close()
+        del dev_sets, host_sets
+        torch.cuda.empty_cache()
+        configs = {}
+        ksteps = max(10, min(args.steps, 30))
+        mr = lambda name, n, nsets, **kw: measure_resident(  # noqa: E731
+            ob, capi, sharding, torch, ob.load_preset(WORKLOADS[name]["preset"]), WORKLOADS[name],
+            n, ksteps, args.warmup, nsets, rank, world, local, dev, hbm_peak, **kw)
+        configs["C2_go2_standing_4096"] = mr("go2_standing_4096", 4096, NSETS)
+        configs["C4_walter_sr_wheels_stairs_8192_per_gpu"] = mr(
+            "walter_sr_wheels_stairs_8192_per_gpu", 8192, NSETS, with_dual=True)
+        sweep = []
+        for n in (1024, 4096, 65536, 131072):  # 16384 per GPU is the headline itself
+            sweep.append(mr(DEFAULT_WORKLOAD, n, 2 if n > 16384 else NSETS))
+        configs["C5_walter_sr_sweep_per_gpu"] = sweep
+        if world == 1:
+            wl1 = WORKLOADS["walter_sr_standing_4096"]
+            configs["C1_walter_sr_standing_one_robot"] = one_robot_latency(
+                ob, capi, ob.load_preset(wl1["preset"]), wl1, local)
 
     if rank != 0:
         if world > 1:
@@ -340,15 +584,9 @@ def main():
         return
 
     # ---- rooflines
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     dfma_peak = capi.measure_dfma_tflops(local)
-    flops = algorithmic_flops_per_solve(spec, k_mean) * n_envs
+    flops = algorithmic_flops_per_solve(spec, res["iters"]) * n_envs
     solve_tflops = flops / (kt.solve_ms * 1e-3) / 1e12
     build_gbs = build_bytes_per_solve(spec) * n_envs / (kt.build_ms * 1e-3) / 1e9
     traffic = {}
@@ -400,7 +638,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms,
                     "wall_ms_per_step": e2e_wall_ms, "host_input_bytes_per_step": in_bytes,
-                    "pcie_h2d_gbs": e2e_h2d / (e2e_ms * 1e-3) / 1e9},
+                    "pcie_h2d_gbs": e2e_h2d / (e2e_ms * 1e-3) / 1e9,
+                    "pcie_h2d_gbs_per_rank": pcie_per_rank, "numa_node_per_rank": numa_per_rank,
+                    "limit": "PCIe: the OSCData record (M, J, bias, ...) is 13.4 kB per environment "
+                             "and crosses the host link every step; at N > 1 ranks that share a "
+                             "PCIe switch / socket share its bandwidth (see per-rank rates)"},
             "gpu_launches": int(stats["launches"]),
             "roofline": roofline, "roofline_scale": roofline_scale,
             "roofline_build": roofline_build,
@@ -410,12 +652,27 @@ def main():
             "solved_frac": stats["solved"] / (world * n_envs),
             "cold_start": {"ms_per_step": cold_ms, "value": world * n_envs / (cold_ms * 1e-3),
                            "iters_mean": cold_iters},
-            "torque_all_gather_ms": gather_ms}
+            "value_incl_gather": value_incl_gather, "ms_per_step_incl_gather": ms_incl,
+            "torque_all_gather_ms": gather_ms,
+            "gather": {"how": "peer stores over NVLink into CUDA-IPC-mapped slabs (osc_gather_torques,"
+                              " one kernel, no collective call)", "ms": gather_ms,
+                       "bytes_per_rank": n_envs * spec.nu * 8 * world, "check_vs_nccl": gather_check,
+                       "nccl_all_gather_into_tensor_ms": nccl_gather_ms,
+                       "stats_all": {k: [float(v) for v in gstats[:, i]]
+                                     for i, k in enumerate(capi.GATHER_STAT_NAMES)}},
+            "numa": numa}
+    if configs is not None:
+        line["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
+        if orig_affinity:
+            try:
+                os.sched_setaffinity(0, orig_affinity)  # the CPU arm gets every host core
+            except Exception:
+                pass
         sample = min(n_envs, 2048)
         _, info = cpu_leg(spec, wl, sample, steps=40, warmup=2)
         line["cpu_baseline"] = info
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -248,6 +248,32 @@ int osc_contact_mask_from_contacts(osc_handle *h, const int *geom_pairs, const i
  * Synchronises `stream`. */
 int osc_reinit_count(osc_handle *h, int *count, void *stream);
 
+/* ---- multi-GPU: the all-gather of torques and statistics after a step (the
+ * reference has no counterpart -- one controller, one robot, one thread).  Environments are
+ * sharded, one handle (and normally one process) per GPU; there is no collective on the hot
+ * path.  The gather is done with PEER STORES instead of a collective library call: every rank
+ * owns a gathered slab
+ *     torque_all [world][n_envs][nu]   followed by   stats_all [world][OSC_GATHER_STATS]
+ * that the other ranks map (CUDA IPC between processes, plain device pointers inside one
+ * process); osc_gather_torques launches one kernel that writes the rank's slice and its
+ * statistics into every mapped slab over NVLink / NVSwitch.  All ranks must use the same
+ * n_envs.  A rank's view is complete once every rank's kernel has finished: synchronise the
+ * ranks (barrier / events) before reading.
+ *   stats_all[r] = { n_envs, #solved, sum iters, max iters, max pri_res, max dua_res,
+ *                    #re-Inits so far, gather sequence number } of rank r.
+ * Call order: osc_gather_create on every rank -> exchange the 64-byte handles by any means
+ * (MPI, torch.distributed, a file) -> osc_gather_attach -> osc_gather_torques after steps. */
+#define OSC_IPC_HANDLE_BYTES 64
+#define OSC_GATHER_STATS 8
+/* allocates the slab; ipc_handle_out (64 bytes, may be NULL inside one process) names it */
+int osc_gather_create(osc_handle *h, int rank, int world, void *ipc_handle_out);
+/* ipc_handles: world x 64 bytes in rank order (other processes), OR peer_slabs: world device
+ * pointers from osc_gather_buffers of handles in THIS process (entry `rank` is ignored) */
+int osc_gather_attach(osc_handle *h, const void *ipc_handles, double *const *peer_slabs);
+int osc_gather_torques(osc_handle *h, void *stream);
+/* device pointers of this rank's gathered copies */
+int osc_gather_buffers(osc_handle *h, double **torque_all, double **stats_all);
+
 /* number of kernels launched by this handle so far (bench bookkeeping) */
 long long osc_kernel_launches(const osc_handle *h);
 

@@ -597,6 +597,79 @@ contact_mask_kernel(const __grid_constant__ ContactIds ids, const int* __restric
 }
 
 // ---------------------------------------------------------------------------
+// K4 (off the hot path): the "all-gather" of torques and statistics as PEER STORES.  Every
+// rank owns a gathered buffer [world][n_envs][nu] (+ [world][kGatherStats] statistics) that
+// its peers have mapped (CUDA IPC between processes, plain pointers inside one process); a
+// rank pushes its own slice into every mapped copy -- 16-byte stores over NVLink / NVSwitch,
+// no staging, no collective call, no NCCL kernel.  Block 0 reduces the rank's statistics
+// (count, solved, iteration sum / max, residual maxima) and pushes them the same way.
+// ---------------------------------------------------------------------------
+constexpr int kGatherStats = 8;
+constexpr int kMaxPeers = 16;
+struct GatherArgs {
+  double* peer[kMaxPeers];   // base of every rank's gathered slab (own included)
+  const double* torque;      // local torques [n_envs][nu]
+  const int *iters, *status;
+  const double *pri_res, *dua_res;
+  const int* reinits;
+  size_t slice;              // doubles per rank in the torque part = n_envs * nu
+  size_t stats_off;          // offset of the statistics part in a slab
+  int rank, world, n_envs;
+  double step;
+};
+
+__global__ void __launch_bounds__(256) gather_push_kernel(const __grid_constant__ GatherArgs a) {
+  if (blockIdx.x == 0) {
+    // statistics of this rank
+    double cnt = 0, solved = 0, isum = 0, imax = 0, pmax = 0, dmax = 0;
+    for (int e = threadIdx.x; e < a.n_envs; e += blockDim.x) {
+      cnt += 1.0;
+      solved += a.status[e] == 1 ? 1.0 : 0.0;
+      const double it = (double)a.iters[e];
+      isum += it;
+      imax = it > imax ? it : imax;
+      const double pr = a.pri_res[e], du = a.dua_res[e];
+      pmax = pr > pmax ? pr : pmax;
+      dmax = du > dmax ? du : dmax;
+    }
+    __shared__ double red[6][8];
+    double v[6] = {cnt, solved, isum, imax, pmax, dmax};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, v[q], o);
+        v[q] = q < 3 ? v[q] + t : (t > v[q] ? t : v[q]);
+      }
+      if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < kGatherStats) {
+      double r = 0.0;
+      const int q = threadIdx.x;
+      if (q < 6) {
+        for (int w = 0; w < 8; ++w) r = q < 3 ? r + red[q][w] : (red[q][w] > r ? red[q][w] : r);
+      } else if (q == 6) {
+        r = (double)*a.reinits;
+      } else {
+        r = a.step;
+      }
+      for (int p = 0; p < a.world; ++p)
+        a.peer[p][a.stats_off + (size_t)a.rank * kGatherStats + q] = r;
+    }
+    return;
+  }
+  const size_t pairs = a.slice / 2;  // nu is even: 16-byte elements
+  const double2* src = reinterpret_cast<const double2*>(a.torque);
+  for (size_t i = (size_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < pairs;
+       i += (size_t)(gridDim.x - 1) * blockDim.x) {
+    const double2 v = src[i];
+#pragma unroll 4
+    for (int p = 0; p < a.world; ++p)
+      reinterpret_cast<double2*>(a.peer[p] + (size_t)a.rank * a.slice)[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Self-test of the warp primitives osc_core3.cuh is written against (osc_warp.cuh): the
 // device readings of the shuffles, reductions and the DMMA tile product, to be compared
 // with the host emulation the CPU tests run the same core on.
@@ -696,6 +769,13 @@ struct osc_handle {
   std::vector<cudaEvent_t> ev;  // 3 events per recorded step
   size_t ev_used;
   long long launches;
+  // multi-GPU gather by peer stores (osc_gather_*): own slab + the mapped slabs of the peers
+  int g_rank, g_world;
+  double* g_slab;                       // [world][n_envs][nu] torques + [world][8] statistics
+  double* g_peer[osc::kMaxPeers];
+  bool g_ipc_opened[osc::kMaxPeers];
+  bool g_attached;
+  long long g_steps;
   std::string err;
 };
 
@@ -979,6 +1059,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
     }
   }
   h->host_h2d_bytes = h->host_d2h_bytes = 0;
+  h->g_rank = 0; h->g_world = 0; h->g_slab = nullptr; h->g_attached = false; h->g_steps = 0;
+  for (int p = 0; p < osc::kMaxPeers; ++p) { h->g_peer[p] = nullptr; h->g_ipc_opened[p] = false; }
   h->timing = false;
   h->timing_mid = nullptr;
   h->ev_used = 0;
@@ -994,6 +1076,9 @@ int osc_destroy(osc_handle* h) {
   double* d[] = {h->dIn, h->dH, h->dF, h->dState,
                  h->dTorque, h->dX, h->dY, h->dPri, h->dDua, h->dRho, h->dScal};
   for (double* p : d) if (p) cudaFree(p);
+  for (int p = 0; p < osc::kMaxPeers; ++p)
+    if (h->g_ipc_opened[p] && h->g_peer[p]) cudaIpcCloseMemHandle(h->g_peer[p]);
+  if (h->g_slab) cudaFree(h->g_slab);
   if (h->hIn) cudaFreeHost(h->hIn);
   if (h->hTq) cudaFreeHost(h->hTq);
   if (h->dIters) cudaFree(h->dIters);
@@ -1413,6 +1498,122 @@ int osc_contact_mask_from_contacts(osc_handle* h, const int* geom_pairs, const i
                                                                   h->dMask, h->n_envs);
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
+  return OSC_OK;
+}
+
+// ---- multi-GPU gather of torques + statistics by peer stores --------------------------------
+static size_t gather_slab_doubles(const osc_handle* h, int world) {
+  return (size_t)world * h->n_envs * h->nu + (size_t)world * osc::kGatherStats;
+}
+
+int osc_gather_create(osc_handle* h, int rank, int world, void* ipc_handle_out) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (world < 1 || world > osc::kMaxPeers || rank < 0 || rank >= world) {
+    h->err = "osc_gather_create: rank / world out of range (world <= 16)";
+    return OSC_ERR_INVALID;
+  }
+  if (h->g_slab) {
+    h->err = "osc_gather_create: already created";
+    return OSC_ERR_STATE;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == OSC_IPC_HANDLE_BYTES, "IPC handle size");
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  const size_t bytes = gather_slab_doubles(h, world) * sizeof(double);
+  OSC_CUDA(h, cudaMalloc((void**)&h->g_slab, bytes));
+  OSC_CUDA(h, cudaMemset(h->g_slab, 0, bytes));
+  h->g_rank = rank;
+  h->g_world = world;
+  h->g_peer[rank] = h->g_slab;
+  h->g_attached = world == 1;
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t ih;
+    OSC_CUDA(h, cudaIpcGetMemHandle(&ih, h->g_slab));
+    std::memcpy(ipc_handle_out, &ih, sizeof(ih));
+  }
+  return OSC_OK;
+}
+
+int osc_gather_attach(osc_handle* h, const void* ipc_handles, double* const* peer_slabs) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!h->g_slab) {
+    h->err = "osc_gather_attach: osc_gather_create has not been called";
+    return OSC_ERR_STATE;
+  }
+  if (!ipc_handles && !peer_slabs && h->g_world > 1) {
+    h->err = "osc_gather_attach: neither IPC handles nor peer pointers given";
+    return OSC_ERR_INVALID;
+  }
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  for (int p = 0; p < h->g_world; ++p) {
+    if (p == h->g_rank) continue;
+    if (peer_slabs) {  // same process: the peers' slabs are ordinary device pointers
+      if (!peer_slabs[p]) {
+        h->err = "osc_gather_attach: null peer pointer";
+        return OSC_ERR_INVALID;
+      }
+      cudaPointerAttributes pa;
+      OSC_CUDA(h, cudaPointerGetAttributes(&pa, peer_slabs[p]));
+      if (pa.device != h->device) {
+        int can = 0;
+        OSC_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, pa.device));
+        if (!can) {
+          h->err = "osc_gather_attach: no peer access between the two devices";
+          return OSC_ERR_CUDA;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(pa.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+          return OSC_ERR_CUDA;
+        }
+        (void)cudaGetLastError();
+      }
+      h->g_peer[p] = peer_slabs[p];
+    } else {  // another process: map its slab (peer access is enabled by the open call)
+      cudaIpcMemHandle_t ih;
+      std::memcpy(&ih, static_cast<const unsigned char*>(ipc_handles) + (size_t)p * sizeof(ih),
+                  sizeof(ih));
+      void* ptr = nullptr;
+      OSC_CUDA(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+      h->g_peer[p] = static_cast<double*>(ptr);
+      h->g_ipc_opened[p] = true;
+    }
+  }
+  h->g_attached = true;
+  return OSC_OK;
+}
+
+int osc_gather_torques(osc_handle* h, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!h->g_slab || !h->g_attached) {
+    h->err = "osc_gather_torques: osc_gather_create / osc_gather_attach first";
+    return OSC_ERR_STATE;
+  }
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  osc::GatherArgs a{};
+  for (int p = 0; p < h->g_world; ++p) a.peer[p] = h->g_peer[p];
+  a.torque = h->dTorque; a.iters = h->dIters; a.status = h->dStatus;
+  a.pri_res = h->dPri; a.dua_res = h->dDua; a.reinits = h->dCounter + h->n_counters;
+  a.slice = (size_t)h->n_envs * h->nu;
+  a.stats_off = (size_t)h->g_world * a.slice;
+  a.rank = h->g_rank; a.world = h->g_world; a.n_envs = h->n_envs;
+  a.step = (double)(++h->g_steps);
+  const size_t pairs = a.slice / 2;
+  int grid = (int)((pairs + 255) / 256);
+  if (grid > h->sm_count * 4) grid = h->sm_count * 4;
+  osc::gather_push_kernel<<<grid + 1, 256, 0, (cudaStream_t)stream>>>(a);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
+int osc_gather_buffers(osc_handle* h, double** torque_all, double** stats_all) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!h->g_slab) {
+    h->err = "osc_gather_buffers: osc_gather_create has not been called";
+    return OSC_ERR_STATE;
+  }
+  if (torque_all) *torque_all = h->g_slab;
+  if (stats_all) *stats_all = h->g_slab + (size_t)h->g_world * h->n_envs * h->nu;
   return OSC_OK;
 }
 

@@ -29,7 +29,12 @@ EXPORTS = (
     "osc_timing_enable", "osc_timing_read", "osc_download_objective", "osc_reinit_count",
     "osc_targets_pd", "osc_contact_mask_from_contacts", "osc_host_traffic",
     "osc_selftest_warp",
+    "osc_gather_create", "osc_gather_attach", "osc_gather_torques", "osc_gather_buffers",
 )
+IPC_HANDLE_BYTES = 64
+GATHER_STATS = 8
+GATHER_STAT_NAMES = ("n_envs", "solved", "iters_sum", "iters_max", "pri_res_max", "dua_res_max",
+                     "reinits", "sequence")
 
 
 class CRobotSpec(C.Structure):
@@ -120,6 +125,10 @@ def load():
     L.osc_contact_mask_from_contacts.argtypes = [vp, vp, vp, C.c_int, ip, ip, vp]
     L.osc_selftest_warp.argtypes = [C.c_int, dp, dp]
     L.osc_host_traffic.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.osc_gather_create.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.osc_gather_attach.argtypes = [vp, vp, C.POINTER(vp)]
+    L.osc_gather_torques.argtypes = [vp, vp]
+    L.osc_gather_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.osc_timing_enable.argtypes = [vp, C.c_int]
     L.osc_timing_read.argtypes = [vp, C.POINTER(CKernelTimes)]
     _LIB = L
@@ -326,6 +335,35 @@ class BatchedOSC:
             self.h, geom_pairs_dev, ncon_dev, int(max_con), ids.ctypes.data_as(ip),
             sog.ctypes.data_as(ip) if sog is not None else None, stream),
             "osc_contact_mask_from_contacts")
+
+    # -- multi-GPU gather by peer stores (osc_gather_*) -----------------------
+    def gather_create(self, rank: int, world: int) -> bytes:
+        """Allocate this rank's gathered slab; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        self._check(self.L.osc_gather_create(self.h, rank, world, buf), "osc_gather_create")
+        self._g_world = world
+        return bytes(buf)
+
+    def gather_attach(self, ipc_handles: bytes | None = None, peer_slabs=None):
+        """Map the peers' slabs: `ipc_handles` = world x 64 bytes in rank order (other
+        processes) or `peer_slabs` = device pointers of handles in this process."""
+        arr = None
+        if peer_slabs is not None:
+            arr = (C.c_void_p * len(peer_slabs))(*[C.c_void_p(int(p) if p else 0) for p in peer_slabs])
+        raw = None
+        if ipc_handles is not None:
+            raw = (C.c_ubyte * len(ipc_handles)).from_buffer_copy(ipc_handles)
+        self._check(self.L.osc_gather_attach(self.h, raw, arr), "osc_gather_attach")
+
+    def gather_torques(self, stream=None):
+        """Push this rank's torques + statistics into every rank's gathered slab."""
+        self._check(self.L.osc_gather_torques(self.h, stream), "osc_gather_torques")
+
+    def gather_buffers(self):
+        """(torque_all, stats_all) device pointers of this rank's gathered copies."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.L.osc_gather_buffers(self.h, C.byref(a), C.byref(b)), "osc_gather_buffers")
+        return a.value, b.value
 
     def host_traffic(self):
         """(h2d_bytes, d2h_bytes) of the last step() / step_host_into()."""

@@ -1,7 +1,10 @@
 """Multi-GPU plumbing: environments are independent, so the hot path has NO collective.
 Each rank owns a contiguous range of environments (one process and one osc_handle per
-GPU); after the step one all-gather collects torques (NCCL over NVLink on GPUs, gloo in the
-CPU tests) and a small all-reduce collects statistics.  SURVEY.md 8(e)."""
+GPU).  After a step the torques and per-rank statistics are gathered by PEER STORES behind the
+C-ABI (osc_gather_*: every rank writes its slice into the slabs its peers exported through
+CUDA IPC); this module only moves the 64-byte handles between the ranks (`exchange_bytes`,
+any torch.distributed backend) and keeps the torch.distributed all-gather / all-reduce used
+by the CPU tests and as the cross-check of the peer-store path.  SURVEY.md 8(e)."""
 from __future__ import annotations
 
 import torch
@@ -33,6 +36,25 @@ def all_gather_rows(local: torch.Tensor, total_rows: int, world: int) -> torch.T
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return torch.cat([o[:c] for o, c in zip(out, counts)], 0)
+
+
+def exchange_bytes(local: bytes, world: int, device=None) -> bytes:
+    """All ranks' fixed-size byte strings concatenated in rank order (the CUDA IPC handles of
+    osc_gather_create).  Works on gloo (CPU tensors) and nccl (pass the CUDA device)."""
+    if world == 1:
+        return bytes(local)
+    t = torch.tensor(list(local), dtype=torch.uint8, device=device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return b"".join(bytes(o.cpu().tolist()) for o in out)
+
+
+def setup_peer_gather(osc, rank: int, world: int, device=None):
+    """osc_gather_create + handle exchange + osc_gather_attach for one-process-per-GPU jobs."""
+    mine = osc.gather_create(rank, world)
+    if world > 1:
+        osc.gather_attach(ipc_handles=exchange_bytes(mine, world, device))
+        dist.barrier()  # nobody pushes before every slab is mapped everywhere
 
 
 def reduce_stats(stats: dict, world: int, device=None) -> dict:

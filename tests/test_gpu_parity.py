@@ -47,9 +47,16 @@ def _oracle_steps(oracle, spec, n_envs, steps, **kw):
     return out
 
 
-def _compare(gpu, orc, tag):
-    keep = orc["repro"] if "repro" in orc else orc["margin"] > 1e-6
-    assert keep.mean() > 0.99, (tag, keep.mean())
+def _compare(gpu, orc, tag, gate="all"):
+    """gate="all": EVERY environment is held to the gates (OSQP default settings: measured
+    100 % at every BASELINE size, profiles/parity_r2.md).  gate="repro": only the
+    environments on which the oracle's own two linear solvers agree -- kept for the
+    tight-tolerance / odd-schedule settings variants, where they part on some."""
+    if gate == "all":
+        keep = np.ones(len(orc["iters"]), bool)
+    else:
+        keep = orc["repro"] if "repro" in orc else orc["margin"] > 1e-6
+        assert keep.mean() > 0.99, (tag, keep.mean())
     assert np.array_equal(gpu["iters"][keep], orc["iters"][keep]), tag
     assert np.array_equal(gpu["status"][keep], orc["status"][keep]), tag
     d = np.abs(gpu["torque"][keep] - orc["torque"][keep])
@@ -378,10 +385,9 @@ def test_ragged_batch_sizes(oracle, n_envs):
     for t, inp in enumerate(steps):
         g.step(inp)
         r = g.results()
-        keep = ref[t]["repro"]
-        assert np.array_equal(r["iters"][keep], ref[t]["iters"][keep])
-        d = np.abs(r["torque"] - ref[t]["torque"])[keep]
-        tol = (ATOL + RTOL * np.abs(ref[t]["torque"]))[keep]
+        assert np.array_equal(r["iters"], ref[t]["iters"])  # every environment, no filter
+        d = np.abs(r["torque"] - ref[t]["torque"])
+        tol = ATOL + RTOL * np.abs(ref[t]["torque"])
         assert (d <= tol).all()
 
 
@@ -442,10 +448,10 @@ def test_parity_at_baseline_sizes(oracle, preset, config, n_envs):
               f"iters equal (all) {same_it.mean():.5f}, within tol (all) {(ratio <= 1).mean():.5f}, "
               f"worst ratio (gated) {ratio[keep].max():.3g}, iters mean {o['iters'].mean():.1f}, "
               f"solved {(r['status'] == capi.SOLVED).mean():.5f}")
-        assert keep.mean() > 0.99
-        assert same_it[keep].all()
-        assert np.array_equal(r["status"][keep], o["status"][keep])
-        assert (ratio[keep] <= 1).all()
+        # default settings: EVERY environment is gated (no reproducible-set filter)
+        assert same_it.all()
+        assert np.array_equal(r["status"], o["status"])
+        assert (ratio <= 1).all()
 
 
 def test_targets_pd_and_contact_mask_kernels_match_oracle(oracle):
@@ -656,11 +662,11 @@ def test_long_horizon_parity(oracle, preset, config):
         g.step(inp)
         r = g.results()
         o = ref[t]
-        alive &= o["repro"]
-        assert np.array_equal(r["iters"][alive], o["iters"][alive]), t
-        assert np.array_equal(r["status"][alive], o["status"][alive]), t
-        d = np.abs(r["torque"] - o["torque"])[alive]
-        tol = (ATOL + RTOL * np.abs(o["torque"]))[alive]
+        alive &= o["repro"]  # reported only: every environment is gated at every tick
+        assert np.array_equal(r["iters"], o["iters"]), t
+        assert np.array_equal(r["status"], o["status"]), t
+        d = np.abs(r["torque"] - o["torque"])
+        tol = ATOL + RTOL * np.abs(o["torque"])
         assert (d <= tol).all(), (t, (d / tol).max())
         worst = max(worst, float((d / tol).max()))
     assert alive.mean() > 0.9, alive.mean()
@@ -771,3 +777,52 @@ def test_longest_first_solve_order_changes_nothing_but_the_schedule(oracle):
         d = np.abs(r["torque"] - o["torque"])[alive]
         assert (d <= (ATOL + RTOL * np.abs(o["torque"]))[alive]).all(), (t, d.max())
     assert alive.mean() > 0.9 and spread >= 25, (alive.mean(), spread)
+
+
+def test_peer_store_gather_of_torques_and_statistics():
+    """osc_gather_*: the all-gather of torques + statistics as peer stores.  Two ranks' handles
+    live on the one GPU of the test box and map each other's slabs by pointer (the
+    same-process route of osc_gather_attach; between processes the same kernel writes through
+    CUDA-IPC mappings -- bench.py checks that route against an NCCL all-gather at N > 1)."""
+    import torch
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr_true_tumbling_mjjoint")
+    n_envs, world = 777 + 1, 2          # not a multiple of the block size
+    hs, tqs, res = [], [], []
+    for r in range(world):
+        inp = ob.synth.make_inputs(spec, n_envs, "tumbling", seed=10 + r)
+        g = capi.BatchedOSC(spec, n_envs)
+        g.setup(inp)
+        tqs.append(g.step(inp))
+        res.append(g.results())
+        assert len(g.gather_create(r, world)) == capi.IPC_HANDLE_BYTES
+        hs.append(g)
+    with pytest.raises(capi.OscError):
+        hs[0].gather_torques()          # peers not attached yet
+    slabs = [g.gather_buffers()[0] for g in hs]
+    for g in hs:
+        g.gather_attach(peer_slabs=slabs)
+    for g in hs:
+        g.gather_torques()
+    torch.cuda.synchronize()
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+
+    def read(ptr, n):
+        out = np.empty(n)
+        assert rt.cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(ptr), C.c_size_t(8 * n), 2) == 0
+        return out
+
+    want = np.concatenate(tqs, 0)
+    for g in hs:
+        t_ptr, s_ptr = g.gather_buffers()
+        got = read(t_ptr, world * n_envs * spec.nu).reshape(world * n_envs, spec.nu)
+        assert np.array_equal(got, want)
+        st = read(s_ptr, world * capi.GATHER_STATS).reshape(world, capi.GATHER_STATS)
+        for r in range(world):
+            assert st[r, 0] == n_envs
+            assert st[r, 1] == (res[r]["status"] == capi.SOLVED).sum()
+            assert st[r, 2] == res[r]["iters"].sum() and st[r, 3] == res[r]["iters"].max()
+            assert st[r, 4] == res[r]["pri_res"].max() and st[r, 5] == res[r]["dua_res"].max()
+            assert st[r, 6] == 0 and st[r, 7] == 1

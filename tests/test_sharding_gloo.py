@@ -31,6 +31,11 @@ def _worker(rank, world, port, q):
     stats = sharding.reduce_stats(dict(solved=int((o["status"] == 1).sum()),
                                        iters=int(o["iters"].sum())), world)
     t = sharding.max_over_ranks(1.0 + rank)
+    # the 64-byte CUDA IPC handles of osc_gather_create travel through exchange_bytes
+    mine = bytes([(7 * rank + i) % 251 for i in range(64)])
+    allh = sharding.exchange_bytes(mine, world)
+    assert len(allh) == 64 * world and allh[64 * rank:64 * rank + 64] == mine
+    assert allh[64 * (1 - rank):64 * (1 - rank) + 64] == bytes([(7 * (1 - rank) + i) % 251 for i in range(64)])
     if rank == 0:
         q.put((tq.numpy(), stats, t))
     dist.barrier()
