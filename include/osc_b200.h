@@ -185,6 +185,22 @@ int osc_selftest_warp(int device, const double *in, double *out);
  * (torques). */
 int osc_host_traffic(const osc_handle *h, size_t *h2d_bytes, size_t *d2h_bytes);
 
+/* ---- CONDENSED fast mode (BASELINE.json north_star subsystems (1) and (2); reported
+ * separately, NEVER the path that is gated against the reference's OSQP iterates).  The
+ * reference keeps  M dv + C = B u + Jc z  as equality rows (walter_sr/autogen/autogen.py:82-93);
+ * dv is unbounded (operational_space_controller.h:286-287), so it can be eliminated exactly:
+ * Cholesky of M, G = M^-1 [B Jc], QP in (u, z) only with P' = G' Hd G + R (n' = nu + 3 nc
+ * variables, 4 nc + n' rows).  Same unique optimum, different ADMM iterates: its torques are
+ * a solution of the same QP to the same OSQP tolerances, not the reference's iterate.  Its
+ * oracle is oracle/osc_condensed.py.  Every step is osqp_setup on the new condensed data with
+ * rho carried over, osqp_warm_start(previous solution), osqp_solve (the shape of the
+ * reference's re-Init branch, :571-584).  No osc_setup needed.  Outputs go to the same
+ * buffers as osc_step: torque, solution = [G w + d0; u; z], dual (friction and box rows; the
+ * eliminated dynamics rows and the free dv rows report 0), iters, status, residuals, rho. */
+int osc_step_condensed(osc_handle *h, void *stream);
+/* cold start (zero warm start, rho = settings.rho) for the next osc_step_condensed */
+int osc_reset_condensed(osc_handle *h, void *stream);
+
 /* Use caller-owned DEVICE memory as the inputs of subsequent osc_setup/osc_step calls
  * (same layouts; NULL keeps the handle's own buffer for that field).  Lets a rollout
  * loop or a benchmark keep several batches resident in HBM without copies. */

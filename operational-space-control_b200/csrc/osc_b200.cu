@@ -51,6 +51,7 @@ __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 #endif
 
 #include "osc_params.h"
+#include "osc_condensed.cuh"
 
 namespace osc {
 
@@ -481,6 +482,79 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// K1 + K3 of the CONDENSED fast mode (osc::CoreC, osc_condensed.cuh): Cholesky of M, G =
+// M^-1 [B Jc], the (u, z)-only QP with P' = G' Hd G + R, OSQP-style scaling / ADMM on n' = nu +
+// 3 nc variables with K^-1 register resident.  One warp per environment, persistent CTAs,
+// dynamic work counter, the environment's record landed by TMA bulk copies.
+// ---------------------------------------------------------------------------
+struct CondArgs {
+  const double *M, *C, *J, *mask, *Hdv, *fdv;
+  double* state;  // [n_envs][WorkspaceC::STATE]: previous w, dual, rho, flag
+  double *torque, *sol_x, *sol_y, *pri_res, *dua_res, *rho;
+  int *iters, *status;
+  unsigned* counter;
+  unsigned base;
+  const int* order;
+  int n_envs;
+};
+
+template <class D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+condensed_kernel(const __grid_constant__ Params p, const CondArgs a) {
+  using WS = WorkspaceC<D>;
+  using CC = CoreC<D>;
+  constexpr int NV = D::NV;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WS* wsb = reinterpret_cast<WS*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WARPS * sizeof(WS));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WS& w = wsb[warp];
+  uint64_t* bar = &bars[warp];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  constexpr uint32_t kBytes = sizeof(typename WS::Stage);
+  static_assert(sizeof(typename WS::Stage) ==
+                    sizeof(double) * (2 * NV * NV + D::NZ * NV + 2 * NV + D::NC + WS::STATE),
+                "the landing stage is exactly the seven bulk copies");
+  uint32_t parity = 0;
+  for (;;) {
+    int env = 0;
+    if (lane == 0) {
+      const int t = (int)(atomicAdd(a.counter, 1u) - a.base);
+      env = (a.order && t < a.n_envs) ? a.order[t] : t;
+      if (env < a.n_envs) {
+        fence_proxy_async();  // the stage was written through the generic proxy (L over M)
+        mbar_expect_tx(bar, kBytes);
+        bulk_g2s(w.in.M, a.M + (size_t)env * NV * NV, sizeof(w.in.M), bar);
+        bulk_g2s(w.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(w.in.H), bar);
+        bulk_g2s(w.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(w.in.Jc), bar);
+        bulk_g2s(w.in.Cv, a.C + (size_t)env * NV, sizeof(w.in.Cv), bar);
+        bulk_g2s(w.in.fv, a.fdv + (size_t)env * NV, sizeof(w.in.fv), bar);
+        bulk_g2s(w.in.maskv, a.mask + (size_t)env * D::NC, sizeof(w.in.maskv), bar);
+        bulk_g2s(w.in.st, a.state + (size_t)env * WS::STATE, sizeof(w.in.st), bar);
+      }
+    }
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= a.n_envs) break;
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const Result r = CC::step(w, p, lane, a.sol_x + (size_t)env * D::N, a.sol_y + (size_t)env * D::M,
+                              a.torque + (size_t)env * D::NU, a.state + (size_t)env * WS::STATE);
+    if (lane == 0) {
+      a.iters[env] = r.iter;
+      a.status[env] = r.status;
+      a.pri_res[env] = r.pri_res;
+      a.dua_res[env] = r.dua_res;
+      a.rho[env] = r.rho;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Longest-processing-time-first order for solve_kernel3's work counter.  The kernel's
 // duration is bounded below by its slowest environment; iteration counts of warm-started
 // control steps are persistent (the ill-conditioned environments stay so), so every few
@@ -622,6 +696,7 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const __grid_constant_
   if (blockIdx.x == 0) {
     // statistics of this rank
     double cnt = 0, solved = 0, isum = 0, imax = 0, pmax = 0, dmax = 0;
+#pragma unroll 8
     for (int e = threadIdx.x; e < a.n_envs; e += blockDim.x) {
       cnt += 1.0;
       solved += a.status[e] == 1 ? 1.0 : 0.0;
@@ -744,6 +819,7 @@ struct osc_handle {
   double *hIn, *hTq;                  // pinned staging of that path (allocated on first use)
   double *dM, *dC, *dJ, *dBias, *dTargets, *dMask;
   double *dH, *dF, *dState, *dScal;
+  double* dStateC;  // condensed fast mode: previous w, dual, rho, flag per environment
   double *dTorque, *dX, *dY, *dPri, *dDua, *dRho;
   int *dIters, *dStatus, *dCounter;
   std::vector<unsigned> ctr_base;  // first ticket of the next launch on every work counter
@@ -924,6 +1000,49 @@ int launch_solve(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
   return launch_solve3<D>(h, st, env0, n, counter);
 }
 
+// condensed_kernel: warps per CTA.  12 at 168 registers is the default; the developer knob
+// OSC_B200_COND_WARPS (environment, read once) selects 8 / 10 / 12 / 15 for occupancy experiments.
+template <class D, int WARPS>
+int launch_condensed_w(osc_handle* h, cudaStream_t st, int n) {
+  static_assert(WARPS * sizeof(osc::WorkspaceC<D>) + 256 <= 227 * 1024, "shared memory per CTA");
+  const size_t smem = WARPS * sizeof(osc::WorkspaceC<D>) + WARPS * sizeof(uint64_t);
+  auto kern = osc::condensed_kernel<D, WARPS>;
+  OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = h->sm_count;
+  const int need = (n + WARPS - 1) / WARPS;
+  if (grid > need) grid = need;
+  const int slot = 2 * h->n_counters + 1;  // last work counter: the condensed launches
+  osc::CondArgs a;
+  a.M = h->iM; a.C = h->iC; a.J = h->iJ; a.mask = h->iMask; a.Hdv = h->dH; a.fdv = h->dF;
+  a.state = h->dStateC;
+  a.torque = h->dTorque; a.sol_x = h->dX; a.sol_y = h->dY;
+  a.pri_res = h->dPri; a.dua_res = h->dDua; a.rho = h->dRho;
+  a.iters = h->dIters; a.status = h->dStatus;
+  a.counter = reinterpret_cast<unsigned*>(h->dCounter) + slot;
+  a.base = h->ctr_base[slot];
+  a.order = h->use_order ? h->dOrder : nullptr;
+  a.n_envs = n;
+  kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
+  OSC_CUDA(h, cudaGetLastError());
+  h->ctr_base[slot] += (unsigned)n + (unsigned)(grid * WARPS);
+  h->launches++;
+  return OSC_OK;
+}
+
+template <class D>
+int launch_condensed(osc_handle* h, cudaStream_t st, int n) {
+  static const int warps = [] {
+    const char* e = std::getenv("OSC_B200_COND_WARPS");
+    return e ? std::atoi(e) : 12;
+  }();
+  switch (warps) {
+    case 8: return launch_condensed_w<D, 8>(h, st, n);
+    case 10: return launch_condensed_w<D, 10>(h, st, n);
+    case 15: return launch_condensed_w<D, 15>(h, st, n);
+    default: return launch_condensed_w<D, 12>(h, st, n);
+  }
+}
+
 #define OSC_DISPATCH(h, fn, ...)                                                    \
   ((h)->shape == osc::Shape::kWalter ? fn<osc::WalterDims>(__VA_ARGS__)             \
                                      : fn<osc::Go2Dims>(__VA_ARGS__))
@@ -1034,11 +1153,11 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   h->n_counters = 64;
   // work counters of the solve launches [0, n), the re-Init count [n], work counters of the
   // scale launches [n + 1, 2n + 1)
-  if ((ce = cudaMalloc((void**)&h->dCounter, (2 * h->n_counters + 1) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
+  if ((ce = cudaMalloc((void**)&h->dCounter, (2 * h->n_counters + 2) * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");
   if ((ce = cudaEventCreateWithFlags(&h->fence_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
-  cudaMemset(h->dCounter, 0, (2 * h->n_counters + 1) * sizeof(int));
-  h->ctr_base.assign(2 * h->n_counters + 1, 0u);
+  cudaMemset(h->dCounter, 0, (2 * h->n_counters + 2) * sizeof(int));
+  h->ctr_base.assign(2 * h->n_counters + 2, 0u);
   if ((ce = cudaMalloc((void**)&h->dOrder, N * sizeof(int))) != cudaSuccess) return fail(ce, "cudaMalloc");
   h->order_age = -1;  // no order yet
   h->use_order = false;
@@ -1059,6 +1178,7 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
     }
   }
   h->host_h2d_bytes = h->host_d2h_bytes = 0;
+  h->dStateC = nullptr;
   h->g_rank = 0; h->g_world = 0; h->g_slab = nullptr; h->g_attached = false; h->g_steps = 0;
   for (int p = 0; p < osc::kMaxPeers; ++p) { h->g_peer[p] = nullptr; h->g_ipc_opened[p] = false; }
   h->timing = false;
@@ -1079,6 +1199,7 @@ int osc_destroy(osc_handle* h) {
   for (int p = 0; p < osc::kMaxPeers; ++p)
     if (h->g_ipc_opened[p] && h->g_peer[p]) cudaIpcCloseMemHandle(h->g_peer[p]);
   if (h->g_slab) cudaFree(h->g_slab);
+  if (h->dStateC) cudaFree(h->dStateC);
   if (h->hIn) cudaFreeHost(h->hIn);
   if (h->hTq) cudaFreeHost(h->hTq);
   if (h->dIters) cudaFree(h->dIters);
@@ -1177,6 +1298,72 @@ int osc_step(osc_handle* h, void* stream) {
   if (ordered) h->order_age++;
   h->kernels_ready = true;  // function attributes / occupancy are set from here on
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[3], st));
+  return OSC_OK;
+}
+
+// ---- condensed fast mode ---------------------------------------------------------------------
+static int condensed_state(osc_handle* h) {
+  if (h->dStateC) return OSC_OK;
+  const size_t ss = h->shape == osc::Shape::kWalter ? osc::WorkspaceC<osc::WalterDims>::STATE
+                                                    : osc::WorkspaceC<osc::Go2Dims>::STATE;
+  const size_t bytes = (size_t)h->n_envs * ss * sizeof(double);
+  OSC_CUDA(h, cudaMalloc((void**)&h->dStateC, bytes));
+  OSC_CUDA(h, cudaMemset(h->dStateC, 0, bytes));
+  return OSC_OK;
+}
+
+int osc_step_condensed(osc_handle* h, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  int rc = condensed_state(h);
+  if (rc) return rc;
+  const bool ordered = h->n_envs > h->sm_count * 12;
+  if (ordered && (h->order_age < 0 || h->order_age >= kOrderEvery)) {
+    osc::order_kernel<<<1, 1024, 0, st>>>(h->dIters, h->n_envs, h->dOrder);
+    OSC_CUDA(h, cudaGetLastError());
+    h->launches++;
+    h->order_age = 0;
+  }
+  cudaEvent_t* ev = nullptr;
+  if (h->timing) {
+    if (h->ev_used + 4 > h->ev.size()) {
+      for (int i = 0; i < 4; ++i) {
+        cudaEvent_t e;
+        OSC_CUDA(h, cudaEventCreate(&e));
+        h->ev.push_back(e);
+      }
+    }
+    ev = &h->ev[h->ev_used];
+    h->ev_used += 4;
+    OSC_CUDA(h, cudaEventRecord(ev[0], st));
+  }
+  rc = OSC_DISPATCH(h, launch_build, h, st, 0, h->n_envs);
+  if (rc) return rc;
+  if (ev) {
+    OSC_CUDA(h, cudaEventRecord(ev[1], st));
+    OSC_CUDA(h, cudaEventRecord(ev[2], st));  // no separate scale kernel in this mode
+  }
+  h->use_order = ordered;
+  rc = OSC_DISPATCH(h, launch_condensed, h, st, h->n_envs);
+  h->use_order = false;
+  if (rc) return rc;
+  if (ordered) h->order_age++;
+  h->kernels_ready = true;
+  if (ev) OSC_CUDA(h, cudaEventRecord(ev[3], st));
+  return OSC_OK;
+}
+
+int osc_reset_condensed(osc_handle* h, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  int rc = condensed_state(h);
+  if (rc) return rc;
+  const size_t ss = h->shape == osc::Shape::kWalter ? osc::WorkspaceC<osc::WalterDims>::STATE
+                                                    : osc::WorkspaceC<osc::Go2Dims>::STATE;
+  OSC_CUDA(h, cudaMemsetAsync(h->dStateC, 0, (size_t)h->n_envs * ss * sizeof(double),
+                              (cudaStream_t)stream));
+  h->order_age = -1;
   return OSC_OK;
 }
 

@@ -30,6 +30,7 @@ EXPORTS = (
     "osc_targets_pd", "osc_contact_mask_from_contacts", "osc_host_traffic",
     "osc_selftest_warp",
     "osc_gather_create", "osc_gather_attach", "osc_gather_torques", "osc_gather_buffers",
+    "osc_step_condensed", "osc_reset_condensed",
 )
 IPC_HANDLE_BYTES = 64
 GATHER_STATS = 8
@@ -129,6 +130,8 @@ def load():
     L.osc_gather_attach.argtypes = [vp, vp, C.POINTER(vp)]
     L.osc_gather_torques.argtypes = [vp, vp]
     L.osc_gather_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.osc_step_condensed.argtypes = [vp, vp]
+    L.osc_reset_condensed.argtypes = [vp, vp]
     L.osc_timing_enable.argtypes = [vp, C.c_int]
     L.osc_timing_read.argtypes = [vp, C.POINTER(CKernelTimes)]
     _LIB = L
@@ -260,6 +263,14 @@ class BatchedOSC:
         """Hot-loop variant of step(): pre-resolved input pointers, caller-owned output."""
         self._check(self.L.osc_step_host(self.h, *ptrs, torque_out.ctypes.data, stream),
                     "osc_step_host")
+
+    def step_condensed(self, stream=None):
+        """Control step of the CONDENSED fast mode on the inputs resident in HBM (Cholesky of
+        M, QP in (u, z) only; reported separately, never the gated path)."""
+        self._check(self.L.osc_step_condensed(self.h, stream), "osc_step_condensed")
+
+    def reset_condensed(self, stream=None):
+        self._check(self.L.osc_reset_condensed(self.h, stream), "osc_reset_condensed")
 
     def reset_warm_start(self, stream=None):
         self._check(self.L.osc_reset_warm_start(self.h, stream), "osc_reset_warm_start")

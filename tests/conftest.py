@@ -32,6 +32,7 @@ def host_core():
     srcs = [os.path.join(d, "host_core.cpp"),
             os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_core.cuh"),
             os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_core3.cuh"),
+            os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_condensed.cuh"),
             os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_warp.cuh"),
             os.path.join(ROOT, "operational-space-control_b200", "csrc", "osc_params.h"),
             os.path.join(ROOT, "include", "osc_b200.h")]

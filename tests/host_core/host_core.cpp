@@ -7,6 +7,7 @@
 #include <type_traits>
 
 #include "../../operational-space-control_b200/csrc/osc_params.h"
+#include "../../operational-space-control_b200/csrc/osc_condensed.cuh"
 
 namespace {
 // added to the linear cost after the objective build: lets a test hand the solver a cost the
@@ -78,7 +79,67 @@ int run(const osc::Params& p, const double* M, const double* C, const double* J,
   info_d[2] = r.rho;
   return 0;
 }
+// the condensed fast mode (csrc/osc_condensed.cuh): one control step of one environment;
+// `state` is the WorkspaceC::STATE-double record (all zeros = cold start), updated in place
+template <class D>
+int run_condensed(const osc::Params& p, const double* M, const double* C, const double* J,
+                  const double* bias, const double* targets, const double* mask, double* state,
+                  double* x, double* y, double* torque, int* info_i, double* info_d) {
+  using Core = osc::CoreC<D>;
+  using WSpace = osc::WorkspaceC<D>;
+  using B = osc::BuildQP<D>;
+  auto ws = std::make_unique<WSpace>();
+  std::memset(ws.get(), 0, sizeof(*ws));
+  for (int a = 0; a < D::NV; ++a) {
+    for (int b = 0; b <= a; ++b) {
+      const double v = B::h_entry(J, p.w_row, p.w_reg, a, b);
+      ws->in.H[a * D::NV + b] = v;
+      ws->in.H[b * D::NV + a] = v;
+    }
+    ws->in.fv[a] = B::f_entry(J, bias, targets, p.w_row, a);
+  }
+  std::memcpy(ws->in.M, M, sizeof(ws->in.M));
+  std::memcpy(ws->in.Jc, J + D::JC0 * D::NV, sizeof(ws->in.Jc));
+  std::memcpy(ws->in.Cv, C, sizeof(ws->in.Cv));
+  std::memcpy(ws->in.maskv, mask, sizeof(ws->in.maskv));
+  std::memcpy(ws->in.st, state, sizeof(ws->in.st));
+  osc::Result r = Core::step(*ws, p, 0, x, y, torque, state);
+  info_i[0] = r.iter;
+  info_i[1] = r.status;
+  info_i[2] = r.rho_updates;
+  info_i[3] = 0;
+  info_d[0] = r.pri_res;
+  info_d[1] = r.dua_res;
+  info_d[2] = r.rho;
+  return 0;
+}
 }  // namespace
+
+extern "C" int osc_condensed_host_state_size(const osc_robot_spec* spec) {
+  switch (osc::shape_of(*spec)) {
+    case osc::Shape::kWalter: return osc::WorkspaceC<osc::WalterDims>::STATE;
+    case osc::Shape::kGo2: return osc::WorkspaceC<osc::Go2Dims>::STATE;
+    default: return -1;
+  }
+}
+
+extern "C" int osc_condensed_host_step(const osc_robot_spec* spec, const osc_settings* settings,
+                                       const double* M, const double* C, const double* J,
+                                       const double* bias, const double* targets,
+                                       const double* mask, double* state, double* x, double* y,
+                                       double* torque, int* info_i, double* info_d) {
+  const osc::Params p = osc::make_params(*spec, *settings);
+  switch (osc::shape_of(*spec)) {
+    case osc::Shape::kWalter:
+      return run_condensed<osc::WalterDims>(p, M, C, J, bias, targets, mask, state, x, y, torque,
+                                            info_i, info_d);
+    case osc::Shape::kGo2:
+      return run_condensed<osc::Go2Dims>(p, M, C, J, bias, targets, mask, state, x, y, torque,
+                                         info_i, info_d);
+    default:
+      return -1;
+  }
+}
 
 extern "C" int osc_core_host_state_size(const osc_robot_spec* spec) {
   switch (osc::shape_of(*spec)) {

@@ -312,3 +312,96 @@ def test_dual_infeasibility_certificate_matches_oracle(oracle, host_core, preset
     np.testing.assert_array_equal(got["status"], [r["status"] for r in ref])
     np.testing.assert_array_equal(got["iters"], [r["iter"] for r in ref])
     assert np.isnan(got["torque"]).all() and np.isnan(got["x"]).all()
+
+
+def run_host_condensed(L, spec, settings, steps, n_envs):
+    from osc_b200 import capi
+    cs = capi.c_spec(spec)
+    SS = L.osc_condensed_host_state_size(C.byref(cs))
+    assert SS == 2 * (spec.nu + 3 * spec.nc) + 4 * spec.nc + 2
+    outs = [dict(torque=np.zeros((n_envs, spec.nu)), iters=np.zeros(n_envs, np.int32),
+                 status=np.zeros(n_envs, np.int32), rho=np.zeros(n_envs),
+                 x=np.zeros((n_envs, spec.n)), y=np.zeros((n_envs, spec.m))) for _ in steps]
+    ii = np.zeros(4, np.int32)
+    dd = np.zeros(3)
+    for e in range(n_envs):
+        state = np.zeros(SS)
+        x = np.zeros(spec.n); y = np.zeros(spec.m); tq = np.zeros(spec.nu)
+        for t, data in enumerate(steps):
+            a = [np.ascontiguousarray(data[k][e]) for k in FIELDS]
+            L.osc_condensed_host_step(C.byref(cs), C.byref(settings), *[_p(v) for v in a],
+                                      _p(state), _p(x), _p(y), _p(tq),
+                                      ii.ctypes.data_as(C.POINTER(C.c_int)), _p(dd))
+            o = outs[t]
+            o["torque"][e], o["x"][e], o["y"][e] = tq, x, y
+            o["iters"][e], o["status"][e], o["rho"][e] = ii[0], ii[1], dd[2]
+    return outs
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_true_tumbling_mjjoint", "tumbling"),
+                                           ("unitree_go2", "go2_standing"),
+                                           ("walter_sr_wheels", "stairs")])
+@pytest.mark.parametrize("kw", [dict(), dict(adaptive_rho_interval=25, eps_abs=1e-5, eps_rel=1e-5),
+                                dict(scaling=0, max_iter=150)],
+                         ids=["defaults", "interval25-eps1e-5", "noscaling"])
+def test_condensed_core_matches_condensed_oracle_on_host(oracle, host_core, preset, config, kw):
+    """The CONDENSED fast mode's device source (csrc/osc_condensed.cuh: Cholesky of M,
+    G = M^-1 [B Jc], P' = G'HdG + R, scaling, K^-1, ADMM) on the emulated warp vs its own
+    oracle (oracle/osc_condensed.py: numpy condensation + the OSQP restatement's generic QP
+    entry): iteration counts and status bit-exact, torques within 1e-5 + 1e-4 |tau|, cold step
+    and two warm steps, both robot shapes."""
+    import osc_b200 as ob
+    import osc_condensed as oc
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    N = 24
+    steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(3)]
+    ref = oc.CondensedOracle(spec, N, oracle.default_settings(**kw))
+    got = run_host_condensed(host_core, spec, capi.default_settings(**kw) if False else
+                             _csettings(kw), steps, N)
+    for t, inp in enumerate(steps):
+        o, g = ref.step(inp), got[t]
+        np.testing.assert_array_equal(g["iters"], o["iters"])
+        np.testing.assert_array_equal(g["status"], o["status"])
+        d = np.abs(g["torque"] - o["torque"])
+        tol = ATOL + RTOL * np.abs(o["torque"])
+        assert (d <= tol).all(), (preset, t, (d / tol).max())
+        np.testing.assert_allclose(g["rho"], o["rho"], rtol=1e-4)
+        # solution in the reference's shape: [dv; u; z] with dv = G w + d0
+        np.testing.assert_allclose(g["x"], o["x"], rtol=1e-3, atol=1e-3 * (1 + np.abs(o["x"]).max()))
+        nv, nu, nc = spec.nv, spec.nu, spec.nc
+        assert np.array_equal(g["torque"], g["x"][:, nv:nv + nu])
+        # the eliminated dynamics hold exactly for the recovered dv
+        Jc = inp["J"][:, 3 * spec.ns - 3 * nc:3 * spec.ns, :]
+        dyn = (np.einsum("bij,bj->bi", inp["M"], g["x"][:, :nv]) + inp["C"]
+               - np.concatenate([np.zeros((N, nv - nu)), g["x"][:, nv:nv + nu]], 1)
+               - np.einsum("bki,bk->bi", Jc, g["x"][:, nv + nu:]))
+        assert np.abs(dyn).max() < 1e-8 * (1 + np.abs(inp["C"]).max())
+
+
+def _csettings(kw):
+    """osc_settings without touching the CUDA library (the CPU suite has no GPU)."""
+    from osc_b200 import capi
+    s = capi.CSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 5.0, 10, 1, 0, 4000, 25, 1)
+    s.eps_prim_inf = s.eps_dual_inf = 1e-4
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_wheels", "stairs"), ("unitree_go2", "go2_standing")])
+def test_condensed_core_has_no_cross_lane_hazard(host_core, host_core_reversed, preset, config):
+    """The race check of test_no_cross_lane_hazard_inside_a_body for csrc/osc_condensed.cuh
+    (in-place Cholesky, per-lane triangular solves, double-buffered exchanges, the two-pivot
+    sweep on whole rows): lanes of every body in the opposite order, bit-identical results."""
+    import osc_b200 as ob
+    spec = ob.load_preset(preset)
+    N = 8
+    steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(2)]
+    st = _csettings(dict(adaptive_rho_interval=25))
+    a = run_host_condensed(host_core, spec, st, steps, N)
+    b = run_host_condensed(host_core_reversed, spec, st, steps, N)
+    for t in range(2):
+        for k in ("torque", "x", "y", "iters", "status", "rho"):
+            assert np.array_equal(a[t][k], b[t][k]), (preset, t, k)
+    assert (a[0]["rho"] != 0.1).any()
