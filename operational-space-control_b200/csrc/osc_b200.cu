@@ -38,7 +38,7 @@
 #include <vector>
 
 #ifdef OSC_PHASE_CLOCKS  // developer build only (tools/phase_clocks.py)
-__device__ unsigned long long g_phase_clocks[24];
+__device__ unsigned long long g_phase_clocks[32];
 __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 #if defined(__CUDA_ARCH__)
   if (lane0 == 0) atomicAdd(&g_phase_clocks[k], (unsigned long long)clock64());
@@ -498,8 +498,12 @@ struct CondArgs {
   int n_envs;
 };
 
+constexpr int cond_max_regs(int warps) {
+  const int r = (65536 / (warps * 32)) / 8 * 8;
+  return r > 255 ? 255 : r;
+}
 template <class D, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(cond_max_regs(WARPS))
 condensed_kernel(const __grid_constant__ Params p, const CondArgs a) {
   using WS = WorkspaceC<D>;
   using CC = CoreC<D>;
@@ -519,6 +523,8 @@ condensed_kernel(const __grid_constant__ Params p, const CondArgs a) {
   static_assert(sizeof(typename WS::Stage) ==
                     sizeof(double) * (2 * NV * NV + D::NZ * NV + 2 * NV + D::NC + WS::STATE),
                 "the landing stage is exactly the seven bulk copies");
+  // (Taking the environments in lockstep batches per CTA, so that the warps share the fetched
+  //  instruction lines, was measured: slower, 0.514 -> 0.562 ms -- profiles/r2_experiments.md.)
   uint32_t parity = 0;
   for (;;) {
     int env = 0;
@@ -528,9 +534,9 @@ condensed_kernel(const __grid_constant__ Params p, const CondArgs a) {
       if (env < a.n_envs) {
         fence_proxy_async();  // the stage was written through the generic proxy (L over M)
         mbar_expect_tx(bar, kBytes);
-        bulk_g2s(w.in.M, a.M + (size_t)env * NV * NV, sizeof(w.in.M), bar);
+        bulk_g2s(w.m(), a.M + (size_t)env * NV * NV, sizeof(double) * NV * NV, bar);
         bulk_g2s(w.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(w.in.H), bar);
-        bulk_g2s(w.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(w.in.Jc), bar);
+        bulk_g2s(w.jc(), a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(double) * D::NZ * NV, bar);
         bulk_g2s(w.in.Cv, a.C + (size_t)env * NV, sizeof(w.in.Cv), bar);
         bulk_g2s(w.in.fv, a.fdv + (size_t)env * NV, sizeof(w.in.fv), bar);
         bulk_g2s(w.in.maskv, a.mask + (size_t)env * D::NC, sizeof(w.in.maskv), bar);
@@ -539,6 +545,7 @@ condensed_kernel(const __grid_constant__ Params p, const CondArgs a) {
     }
     env = __shfl_sync(0xffffffffu, env, 0);
     if (env >= a.n_envs) break;
+    __syncwarp();
     mbar_wait(bar, parity);
     parity ^= 1;
     const Result r = CC::step(w, p, lane, a.sol_x + (size_t)env * D::N, a.sol_y + (size_t)env * D::M,
@@ -839,7 +846,9 @@ struct osc_handle {
   size_t host_h2d_bytes, host_d2h_bytes;  // traffic of the last osc_step_host
   cudaEvent_t timing_mid;  // set while a timed step is being recorded: scale | solve boundary
   int build_grid_max;   // resident CTAs of build_qp_kernel on the device
-  bool kernels_ready;
+  bool kernels_ready;   // function attributes of the scale / solve kernels are set
+  bool build_ready;     // ... of the build kernel (+ its resident grid size)
+  bool cond_ready;      // ... of the condensed kernel
   // optional per-kernel timing
   bool timing;
   std::vector<cudaEvent_t> ev;  // 3 events per recorded step
@@ -874,12 +883,13 @@ int launch_build(osc_handle* h, cudaStream_t st, int env0, int n) {
   const size_t smem = osc::kBuildWarps * osc::kBuildStages * (sizeof(osc::BuildStage<D>) + sizeof(uint64_t)) +
                       kRows * (sizeof(double) + sizeof(int));
   auto kern = osc::build_qp_kernel<D>;
-  if (!h->kernels_ready) {
+  if (!h->build_ready) {
     OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     OSC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     h->build_grid_max = h->sm_count * per_sm;
+    h->build_ready = true;
   }
   int grid = h->build_grid_max;
   const int need = (n + osc::kBuildWarps - 1) / osc::kBuildWarps;
@@ -1007,7 +1017,10 @@ int launch_condensed_w(osc_handle* h, cudaStream_t st, int n) {
   static_assert(WARPS * sizeof(osc::WorkspaceC<D>) + 256 <= 227 * 1024, "shared memory per CTA");
   const size_t smem = WARPS * sizeof(osc::WorkspaceC<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::condensed_kernel<D, WARPS>;
-  OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!h->cond_ready) {
+    OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->cond_ready = true;
+  }
   int grid = h->sm_count;
   const int need = (n + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
@@ -1185,6 +1198,8 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   h->timing_mid = nullptr;
   h->ev_used = 0;
   h->kernels_ready = false;
+  h->build_ready = false;
+  h->cond_ready = false;
   h->build_grid_max = h->sm_count;
   *out = h;
   return OSC_OK;
@@ -1349,7 +1364,6 @@ int osc_step_condensed(osc_handle* h, void* stream) {
   h->use_order = false;
   if (rc) return rc;
   if (ordered) h->order_age++;
-  h->kernels_ready = true;
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[3], st));
   return OSC_OK;
 }
@@ -1591,10 +1605,10 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
 
 #ifdef OSC_PHASE_CLOCKS
 int osc_debug_phase_clocks(unsigned long long* out16, int reset) {
-  if (cudaMemcpyFromSymbol(out16, ::g_phase_clocks, 24 * sizeof(unsigned long long)) != cudaSuccess)
+  if (cudaMemcpyFromSymbol(out16, ::g_phase_clocks, 32 * sizeof(unsigned long long)) != cudaSuccess)
     return OSC_ERR_CUDA;
   if (reset) {
-    unsigned long long z[24] = {0};
+    unsigned long long z[32] = {0};
     if (cudaMemcpyToSymbol(::g_phase_clocks, z, sizeof(z)) != cudaSuccess) return OSC_ERR_CUDA;
   }
   return OSC_OK;

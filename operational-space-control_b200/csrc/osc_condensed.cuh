@@ -40,14 +40,22 @@ struct alignas(16) WorkspaceC {
   static constexpr int STATE = NP + MP + 2; // w, dual (unscaled), rho, flag
   static_assert(STATE % 2 == 0 && NP % 2 == 0, "16-byte records");
   struct alignas(16) Stage {  // landing stage of the bulk copies
-    double M[NV * NV];   // mass_matrix; overwritten by its Cholesky factor L (lower)
+    // mass_matrix (overwritten by its Cholesky factor L, lower) followed by the contact rows
+    // of J (= contact_jacobian'): both are dead once G is known, and the one array then serves
+    // as the lane-private scratch of p_row (SCR doubles)
+    double MJ[NV * NV + NZ * NV];
     double H[NV * NV];   // Hd (build kernel)
-    double Jc[NZ * NV];  // contact rows of J (= contact_jacobian')
     double Cv[NV], fv[NV];
     double maskv[NC];
     double st[STATE];
   };
   Stage in;
+  static constexpr int SCR = 32 * (NP / 2);
+  static_assert(SCR <= NV * NV + NZ * NV, "p_row scratch fits over M and Jc");
+  OSC_HD double* m() { return in.MJ; }
+  OSC_HD const double* m() const { return in.MJ; }
+  OSC_HD double* jc() { return in.MJ + NV * NV; }
+  OSC_HD const double* jc() const { return in.MJ + NV * NV; }
   double Gt[NP * NV];      // G transposed: column j of G contiguous
   double d0[NV], vv[NV];   // -M^-1 C ;  Hd d0 + fd
   double linv[NV];         // 1 / L_ii
@@ -83,29 +91,37 @@ struct CoreC {
     Var<double> pd;                     // scaled diagonal contribution R_jj (for P x)
   };
 
-  // ---- M = L L' in place (lower triangle), 1 / L_ii on the side
+  // ---- M = L L' (lower triangle, written back over M), 1 / L_ii on the side.  Lane i holds
+  //      row i in registers; per column k the pivot comes by shuffle from lane k and the
+  //      scaled column goes through a double-buffered shared-memory vector: one barrier per
+  //      column, no read-modify-write of shared memory.
   static OSC_HD void cholesky(WS& w, const int lane0) {
-    double* A = w.in.M;
-#pragma unroll 1
+    Var<double> a[NV];
+    OSC_LANES(l) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) a[j][l] = l < NV ? w.m()[l * NV + j] : 0.0;
+    }
+    Warp::sync();
+#pragma unroll
     for (int k = 0; k < NV; ++k) {
-      Warp::sync();
+      const double s = C3::inv_sqrt(Warp::bcast(a[k], k));
+      double* col = (k & 1) ? w.bv : w.av;
       OSC_LANES(l) {
-        if (l >= k && l < NV) {
-          const double s = C3::inv_sqrt(A[k * NV + k]);
-          const double v = A[l * NV + k] * s;
-          // (the diagonal keeps its old value until every lane has read it: lane k writes
-          //  sqrt(A_kk) after the barrier below)
-          if (l != k) A[l * NV + k] = v;
-          if (l == k) w.linv[k] = s;
-        }
+        a[k][l] = a[k][l] * s;  // L_lk (lane k: sqrt(A_kk)); rows above k carry don't-cares
+        if (l < NV) col[l] = a[k][l];
+        if (l == k) w.linv[k] = s;
       }
       Warp::sync();
       OSC_LANES(l) {
-        if (l == k) A[k * NV + k] = A[k * NV + k] * w.linv[k];
-        if (l > k && l < NV) {
-          const double lik = A[l * NV + k];
-          for (int j = k + 1; j <= l; ++j) A[l * NV + j] -= lik * A[j * NV + k];
-        }
+#pragma unroll
+        for (int j = k + 1; j < NV; ++j) a[j][l] -= a[k][l] * col[j];  // (entries j > l: unused)
+      }
+    }
+    OSC_LANES(l) {
+      if (l < NV) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+          if (j <= l) w.m()[l * NV + j] = a[j][l];
       }
     }
     Warp::sync();
@@ -114,7 +130,7 @@ struct CoreC {
   // x = M^-1 b for two right-hand sides per lane at once (the lane's column of [B Jc] and -C),
   // L read by broadcast loads
   static OSC_HD void solve2(const WS& w, double (&g)[NV], double (&d)[NV]) {
-    const double* L = w.in.M;
+    const double* L = w.m();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       double s = g[i], t = d[i];
@@ -126,6 +142,7 @@ struct CoreC {
       }
       g[i] = s * w.linv[i];
       d[i] = t * w.linv[i];
+      OSC_COMPILER_BARRIER();
     }
 #pragma unroll
     for (int i = NV - 1; i >= 0; --i) {
@@ -138,12 +155,19 @@ struct CoreC {
       }
       g[i] = s * w.linv[i];
       d[i] = t * w.linv[i];
+      OSC_COMPILER_BARRIER();
     }
   }
 
-  // Row j of P' = G' Hd G + R from G (shared memory) and Hd; q'_j on the side.
-  static OSC_HD void p_row(const WS& w, const Params& p, Regs& L, const int lane0, Var<double>* qout) {
+  // Row j of P' = G' Hd G + R from G (shared memory) and Hd; q'_j on the side.  The loop over
+  // the NP entries of the row is ROLLED (a register array cannot be indexed dynamically, so
+  // the entries go through lane-private scratch slots, half a row at a time): unrolled it was
+  // 1 k instructions of straight-line code per call, and this kernel is instruction-fetch
+  // bound when its warps stream through long unrolled phases (ncu: stall_no_inst).
+  static OSC_HD void p_row(WS& w, const Params& p, Regs& L, const int lane0, Var<double>* qout) {
     const double hu = 2.0 * (p.w_reg + p.w_torque), hz = 2.0 * p.w_reg;
+    double* scr = w.m();
+    constexpr int HALF = NP / 2;
     OSC_LANES(l) {
       const int j = wvar(l);
       const double* gj = &w.Gt[(j >= 0 ? j : 0) * NV];
@@ -160,17 +184,23 @@ struct CoreC {
         t[i] = a0 + a1;
       }
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        double a0 = 0.0, a1 = 0.0;
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+        for (int ii = 0; ii < HALF; ++ii) {
+          const int i = h * HALF + ii;
+          double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < NV; k += 2) {
-          const Pair g = ld2(&w.Gt[i * NV + k]);
-          a0 += g.x * t[k];
-          a1 += g.y * t[k + 1];
+          for (int k = 0; k < NV; k += 2) {
+            const Pair g = ld2(&w.Gt[i * NV + k]);
+            a0 += g.x * t[k];
+            a1 += g.y * t[k + 1];
+          }
+          double v = a0 + a1;
+          if (i == j) v += (j < NU ? hu : hz);
+          scr[ii * 32 + l] = j >= 0 ? v : 0.0;
         }
-        double v = a0 + a1;
-        if (i == j) v += (j < NU ? hu : hz);
-        L.KI[i][l] = j >= 0 ? v : 0.0;
+#pragma unroll
+        for (int ii = 0; ii < HALF; ++ii) L.KI[h * HALF + ii][l] = scr[ii * 32 + l];
       }
       if (qout) {
         double a0 = 0.0, a1 = 0.0;
@@ -185,8 +215,8 @@ struct CoreC {
     }
   }
 
-  // ---- condensation: Cholesky, G, d0, v, then P' rows / q' (registers)
-  static OSC_HD void condense(WS& w, const Params& p, Regs& L, const int lane0, Var<double>& qv) {
+  // ---- condensation: Cholesky, G, d0, v (P' rows / q' follow in p_row)
+  static OSC_HD void condense(WS& w, const Params& p, const int lane0) {
     cholesky(w, lane0);
     OSC_LANES(l) {
       const int j = wvar(l);
@@ -195,7 +225,7 @@ struct CoreC {
       for (int i = 0; i < NV; ++i) {
         double b = 0.0;
         if (j >= 0 && j < NU) b = (i == NB + j) ? 1.0 : 0.0;          // B = [0; I] (autogen.py:54-60)
-        if (j >= NU) b = w.in.Jc[(j - NU) * NV + i];                  // column of Jc (:497-503)
+        if (j >= NU) b = w.jc()[(j - NU) * NV + i];                  // column of Jc (:497-503)
         g[i] = b;
         d[i] = -w.in.Cv[i];
       }
@@ -216,7 +246,6 @@ struct CoreC {
       }
     }
     Warp::sync();
-    p_row(w, p, L, lane0, &qv);
   }
 
   // ---- OSQP scale_data on [P' A''; A' 0] (cumulative form, like Core3::ruiz): D, E_box,
@@ -409,15 +438,19 @@ struct CoreC {
         }
       }
     }
-    // two-pivot symmetric sweep: rows p, q published, everybody updates its row
-#pragma unroll
+    // two-pivot symmetric sweep (Core3::gj_sweep's algorithm on whole rows), the loop over the
+    // pivot pairs ROLLED: instead of indexing the register row by the (dynamic) pivot, every
+    // round rotates the columns left by two while it updates them, so that the pivots are
+    // always columns 0 and 1 and land in columns NP-2, NP-1; after NP/2 rounds the order is
+    // the original one again.  Register t holds column (t + 2 b) mod NP in round b.
+#pragma unroll 1
     for (int b = 0; b < NP / 2; ++b) {
-      const int pp = 2 * b, qq = pp + 1;
+      const int off = 2 * b;
       double* buf = w.pub[b & 1];
       OSC_LANES(l) {
         const int j = wvar(l);
-        if (j == pp || j == qq) {
-          double* d = buf + (j - pp) * NP;
+        if (j == off || j == off + 1) {
+          double* d = buf + (j - off) * NP;
 #pragma unroll
           for (int t = 0; t < NP; t += 2) C3::st2(d + t, L.KI[t][l], L.KI[t + 1][l]);
         }
@@ -427,29 +460,33 @@ struct CoreC {
         const int j = wvar(l);
         const double* rp = buf;
         const double* rq = buf + NP;
-        const Pair bp = ld2(buf + pp);  // A_pp, A_pq
-        const double aqq = buf[NP + qq];
+        const Pair bp = ld2(rp);  // A_pp, A_pq
+        const double aqq = rq[1];
         const double dinv = C3::rcp(bp.x * aqq - bp.y * bp.y);
         const double b11 = aqq * dinv, b12 = -(bp.y * dinv), b22 = bp.x * dinv;
-        const double cp = j >= 0 ? rp[j] : 0.0, cq = j >= 0 ? rq[j] : 0.0;
+        // A_ip == A_pi, A_iq == A_qi up to rounding: taken from the published rows at the
+        // lane's own column (position j - off in the rotated order)
+        int pos = j - off;
+        pos = pos < 0 ? pos + NP : pos;
+        const double cp = j >= 0 ? rp[pos] : 0.0, cq = j >= 0 ? rq[pos] : 0.0;
         double g1 = cp * b11 + cq * b12, g2 = cp * b12 + cq * b22;
-        if (j == pp) {
+        if (j == off) {
           g1 = -b11;
           g2 = -b12;
         }
-        if (j == qq) {
+        if (j == off + 1) {
           g1 = -b12;
           g2 = -b22;
         }
-        const double keep = (j == pp || j == qq) ? 0.0 : 1.0;
+        const double keep = (j == off || j == off + 1) ? 0.0 : 1.0;
 #pragma unroll
-        for (int t = 0; t < NP; t += 2) {
-          const Pair r1 = ld2(rp + t), r2 = ld2(rq + t);
-          L.KI[t][l] = (L.KI[t][l] * keep - g1 * r1.x) - g2 * r2.x;
-          L.KI[t + 1][l] = (L.KI[t + 1][l] * keep - g1 * r1.y) - g2 * r2.y;
+        for (int t = 0; t < NP - 2; t += 2) {
+          const Pair r1 = ld2(rp + t + 2), r2 = ld2(rq + t + 2);
+          L.KI[t][l] = (L.KI[t + 2][l] * keep - g1 * r1.x) - g2 * r2.x;
+          L.KI[t + 1][l] = (L.KI[t + 3][l] * keep - g1 * r1.y) - g2 * r2.y;
         }
-        L.KI[pp][l] = g1;
-        L.KI[qq][l] = g2;
+        L.KI[NP - 2][l] = g1;
+        L.KI[NP - 1][l] = g2;
       }
     }
     OSC_LANES(l) {
@@ -622,74 +659,81 @@ struct CoreC {
   // osqp_solve: same loop structure as Core3::admm (stretches that end with an event
   // iteration).  The condensed QP is always feasible and strictly convex, so the
   // infeasibility certificates of check_termination can never fire and are not evaluated.
-  static OSC_HD Result admm(WS& w, const Params& p, Regs& L, double c, double rho,
-                            const int lane0) {
+  // Resumable: returns false when rho changed and the caller has to rebuild K^-1 (p_row +
+  // factor have ONE call site each, in step(): inlined twice they were 4 k instructions of
+  // a kernel whose warps run through different phases of it at the same time).
+  struct Loop {
+    int iter, to_check, to_adapt, interval;
+    bool adaptive;
+    double rho;
     Result res;
-    res.iter = 0;
-    res.status = kUnsolved;
-    res.rho_updates = 0;
-    res.reinit = 0;
-    int interval = p.adaptive_rho_interval;
-    if (p.adaptive_rho && !interval)
-      interval = p.check_termination ? 4 * p.check_termination : 100;
-    const bool adaptive = p.adaptive_rho && interval;
     Residuals r;
-    r.pri_res = r.dua_res = r.eps_pri_norm = r.eps_dua_norm = r.rho_pri = r.rho_dua = 0.0;
-    int iter = 0, to_check = p.check_termination, to_adapt = interval;
+  };
+  static OSC_HD void admm_begin(const Params& p, Loop& s, double rho) {
+    s.res.iter = 0;
+    s.res.status = kUnsolved;
+    s.res.rho_updates = 0;
+    s.res.reinit = 0;
+    s.interval = p.adaptive_rho_interval;
+    if (p.adaptive_rho && !s.interval)
+      s.interval = p.check_termination ? 4 * p.check_termination : 100;
+    s.adaptive = p.adaptive_rho && s.interval;
+    s.r.pri_res = s.r.dua_res = s.r.eps_pri_norm = s.r.eps_dua_norm = s.r.rho_pri = s.r.rho_dua = 0.0;
+    s.iter = 0;
+    s.to_check = p.check_termination;
+    s.to_adapt = s.interval;
+    s.rho = rho;
+  }
+  static OSC_HD bool admm_run(WS& w, const Params& p, Regs& L, double c, Loop& s, const int lane0) {
     for (;;) {
-      int n = p.max_iter - iter;
-      if (p.check_termination && to_check < n) n = to_check;
-      if (adaptive && to_adapt < n) n = to_adapt;
+      int n = p.max_iter - s.iter;
+      if (p.check_termination && s.to_check < n) n = s.to_check;
+      if (s.adaptive && s.to_adapt < n) n = s.to_adapt;
+      OSC_TICK(27);
 #pragma unroll 1
-      for (int k = 0; k < n; ++k) iterate(w, p, L, w.r1[(iter + k) & 1], lane0);
-      iter += n;
-      to_check -= n;
-      to_adapt -= n;
-      const bool last = iter >= p.max_iter;
-      const bool check = p.check_termination && to_check == 0;
-      const bool adapt = adaptive && to_adapt == 0;
-      if (check) to_check = p.check_termination;
-      if (adapt) to_adapt = interval;
-      r = residuals(w, L, c, lane0);
+      for (int k = 0; k < n; ++k) iterate(w, p, L, w.r1[(s.iter + k) & 1], lane0);
+      OSC_TICK(28);
+      s.iter += n;
+      s.to_check -= n;
+      s.to_adapt -= n;
+      const bool last = s.iter >= p.max_iter;
+      const bool check = p.check_termination && s.to_check == 0;
+      const bool adapt = s.adaptive && s.to_adapt == 0;
+      if (check) s.to_check = p.check_termination;
+      if (adapt) s.to_adapt = s.interval;
+      s.r = residuals(w, L, c, lane0);
       bool ended_at_check = false;
       if (check || last) {
-        if (r.pri_res > kInfty || r.dua_res > kInfty) {
-          res.status = kNonCvx;
+        if (s.r.pri_res > kInfty || s.r.dua_res > kInfty) {
+          s.res.status = kNonCvx;
         } else {
-          const bool ok = r.pri_res < p.eps_abs + p.eps_rel * r.eps_pri_norm &&
-                          r.dua_res < p.eps_abs + p.eps_rel * r.eps_dua_norm;
-          if (ok) res.status = kSolved;
-          else if (last && r.pri_res < 10 * (p.eps_abs + p.eps_rel * r.eps_pri_norm) &&
-                   r.dua_res < 10 * (p.eps_abs + p.eps_rel * r.eps_dua_norm))
-            res.status = kSolvedInaccurate;
+          const bool ok = s.r.pri_res < p.eps_abs + p.eps_rel * s.r.eps_pri_norm &&
+                          s.r.dua_res < p.eps_abs + p.eps_rel * s.r.eps_dua_norm;
+          if (ok) s.res.status = kSolved;
+          else if (last && s.r.pri_res < 10 * (p.eps_abs + p.eps_rel * s.r.eps_pri_norm) &&
+                   s.r.dua_res < 10 * (p.eps_abs + p.eps_rel * s.r.eps_dua_norm))
+            s.res.status = kSolvedInaccurate;
         }
-        ended_at_check = check && res.status != kUnsolved;
+        ended_at_check = check && s.res.status != kUnsolved;
       }
+      bool refactor = false;
       if (adapt && !ended_at_check) {
-        double rho_new = rho * sqrt(r.rho_pri / (r.rho_dua + 1e-10));
+        double rho_new = s.rho * sqrt(s.r.rho_pri / (s.r.rho_dua + 1e-10));
         rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
-        if (rho_new > rho * p.rho_tol || rho_new < rho / p.rho_tol) {
-          rho = rho_new;
-          res.rho_updates++;
-          if (!last) {
-            set_rho(w, L, rho, lane0);
-            p_row(w, p, L, lane0, nullptr);  // K^-1 overwrote the P' row: rebuild it
-            factor(w, p, L, c, lane0);
-          }
+        if (rho_new > s.rho * p.rho_tol || rho_new < s.rho / p.rho_tol) {
+          s.rho = rho_new;
+          s.res.rho_updates++;
+          refactor = !last;
         }
       }
-      if (res.status != kUnsolved) break;
+      if (s.res.status != kUnsolved) return true;
       if (last) {
-        res.status = kMaxIterReached;
-        break;
+        s.res.status = kMaxIterReached;
+        return true;
       }
       Warp::sync();
+      if (refactor) return false;
     }
-    res.iter = iter;
-    res.pri_res = r.pri_res;
-    res.dua_res = r.dua_res;
-    res.rho = rho;
-    return res;
   }
 
   // One control step of one environment.  w.in holds the landed record; out_x [N] gets the
@@ -699,46 +743,70 @@ struct CoreC {
                             double* torque, double* state_out) {
     Regs L;
     Var<double> qv, Dj, Ebj, Efl;
-    condense(w, p, L, lane0, qv);
+    OSC_TICK(17);
+    condense(w, p, lane0);
+    OSC_TICK(18);
     double c = 1.0;
-    if (p.scaling > 0) {
-      c = ruiz(w, p, L, qv, Dj, Ebj, Efl, lane0);
-    } else {
-      OSC_LANES(l) {
-        const int j = wvar(l);
-        if (j >= 0) w.Dv[j] = w.Eb[j] = 1.0;
-        w.Ef[l] = l < NF ? 1.0 : 0.0;
+    Loop lp;
+    bool first = true;
+    for (;;) {
+      // P' row of the lane (the ONE call site: first pass, and again after every rho change,
+      // when K^-1 has overwritten it)
+      OSC_TICK(19);
+      p_row(w, p, L, lane0, first ? &qv : nullptr);
+      OSC_TICK(20);
+      if (first) {
+        first = false;
+        OSC_TICK(21);
+        if (p.scaling > 0) {
+          c = ruiz(w, p, L, qv, Dj, Ebj, Efl, lane0);
+        } else {
+          OSC_LANES(l) {
+            const int j = wvar(l);
+            if (j >= 0) w.Dv[j] = w.Eb[j] = 1.0;
+            w.Ef[l] = l < NF ? 1.0 : 0.0;
+          }
+          Warp::sync();
+        }
+        assemble(w, p, L, qv, c, lane0);
+        const bool have = w.in.st[NP + MP + 1] != 0.0;
+        double rho = have ? w.in.st[NP + MP] : p.rho0;
+        rho = fmin(fmax(rho, kRhoMin), kRhoMax);
+        // osqp_warm_start(x, y): x <- Dinv x, y <- c Einv y, z <- A x  (cold: zeros)
+        const bool warm = have && p.warm_start;
+        OSC_LANES(l) {
+          const int j = wvar(l);
+          L.x[l] = L.yu[l] = L.yf[l] = 0.0;
+          if (warm && j >= 0) {
+            L.x[l] = C3::rcp(w.Dv[j]) * w.in.st[j];
+            L.yu[l] = (C3::rcp(w.Eb[j]) * w.in.st[NP + NF + j]) * c;
+          }
+          if (warm && l < NF) L.yf[l] = (C3::rcp(w.Ef[l]) * w.in.st[NP + l]) * c;
+        }
+        Var<double> x0, x1, x2;
+        Warp::group4(x0, L.x, 0);
+        Warp::group4(x1, L.x, 1);
+        Warp::group4(x2, L.x, 2);
+        OSC_LANES(l) {
+          L.zu[l] = L.ibu[l] * L.x[l];
+          L.zf[l] = L.fr[0][l] * x0[l] + L.fr[1][l] * x1[l] + L.fr[2][l] * x2[l];
+        }
+        admm_begin(p, lp, rho);
+        OSC_TICK(22);
       }
-      Warp::sync();
+      OSC_TICK(23);
+      set_rho(w, L, lp.rho, lane0);
+      factor(w, p, L, c, lane0);
+      OSC_TICK(24);
+      const bool done = admm_run(w, p, L, c, lp, lane0);
+      OSC_TICK(25);
+      if (done) break;
     }
-    assemble(w, p, L, qv, c, lane0);
-    const bool have = w.in.st[NP + MP + 1] != 0.0;
-    double rho = have ? w.in.st[NP + MP] : p.rho0;
-    rho = fmin(fmax(rho, kRhoMin), kRhoMax);
-    // osqp_warm_start(x, y): x <- Dinv x, y <- c Einv y, z <- A x  (cold: zeros)
-    const bool warm = have && p.warm_start;
-    OSC_LANES(l) {
-      const int j = wvar(l);
-      L.x[l] = L.yu[l] = L.yf[l] = 0.0;
-      if (warm && j >= 0) {
-        L.x[l] = C3::rcp(w.Dv[j]) * w.in.st[j];
-        L.yu[l] = (C3::rcp(w.Eb[j]) * w.in.st[NP + NF + j]) * c;
-      }
-      if (warm && l < NF) L.yf[l] = (C3::rcp(w.Ef[l]) * w.in.st[NP + l]) * c;
-    }
-    {
-      Var<double> x0, x1, x2;
-      Warp::group4(x0, L.x, 0);
-      Warp::group4(x1, L.x, 1);
-      Warp::group4(x2, L.x, 2);
-      OSC_LANES(l) {
-        L.zu[l] = L.ibu[l] * L.x[l];
-        L.zf[l] = L.fr[0][l] * x0[l] + L.fr[1][l] * x1[l] + L.fr[2][l] * x2[l];
-      }
-    }
-    set_rho(w, L, rho, lane0);
-    factor(w, p, L, c, lane0);
-    Result res = admm(w, p, L, c, rho, lane0);
+    Result res = lp.res;
+    res.iter = lp.iter;
+    res.pri_res = lp.r.pri_res;
+    res.dua_res = lp.r.dua_res;
+    res.rho = lp.rho;
     // ---- un-scale, recover dv = G w + d0, outputs
     const double cinv = 1.0 / c;
     Warp::sync();
@@ -781,6 +849,7 @@ struct CoreC {
       }
     }
     Warp::sync();
+    OSC_TICK(26);
     return res;
   }
 };

@@ -23,6 +23,14 @@
 #endif
 #endif
 
+// keeps the compiler from moving memory accesses across this point (used where hoisting
+// every load of a long unrolled phase to its top costs more registers than it hides latency)
+#if defined(__CUDA_ARCH__)
+#define OSC_COMPILER_BARRIER() asm volatile("" ::: "memory")
+#else
+#define OSC_COMPILER_BARRIER() ((void)0)
+#endif
+
 namespace osc {
 
 #if defined(__CUDA_ARCH__)
@@ -45,6 +53,10 @@ struct Warp {
   // dst[l] = src[(l & ~3) | r]   (broadcast inside a group of four lanes)
   static OSC_HD void group4(Var<double>& dst, const Var<double>& src, int r) {
     dst.v = __shfl_sync(kFull, src.v, r, 4);
+  }
+  // the value of lane `from` in every lane
+  static OSC_HD double bcast(const Var<double>& src, int from) {
+    return __shfl_sync(kFull, src.v, from);
   }
   static OSC_HD double sum(const Var<double>& a) {
     double v = a.v;
@@ -138,6 +150,7 @@ struct Warp {
     for (int l = 0; l < 32; ++l) t[l] = src.v[(l & ~3) | r];
     for (int l = 0; l < 32; ++l) dst.v[l] = t[l];
   }
+  static double bcast(const Var<double>& src, int from) { return src.v[from]; }
   static double sum(const Var<double>& a) {  // the device's butterfly order
     double v[32], t[32];
     for (int l = 0; l < 32; ++l) v[l] = a.v[l];

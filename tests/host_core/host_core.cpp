@@ -98,8 +98,8 @@ int run_condensed(const osc::Params& p, const double* M, const double* C, const 
     }
     ws->in.fv[a] = B::f_entry(J, bias, targets, p.w_row, a);
   }
-  std::memcpy(ws->in.M, M, sizeof(ws->in.M));
-  std::memcpy(ws->in.Jc, J + D::JC0 * D::NV, sizeof(ws->in.Jc));
+  std::memcpy(ws->m(), M, sizeof(double) * D::NV * D::NV);
+  std::memcpy(ws->jc(), J + D::JC0 * D::NV, sizeof(double) * D::NZ * D::NV);
   std::memcpy(ws->in.Cv, C, sizeof(ws->in.Cv));
   std::memcpy(ws->in.maskv, mask, sizeof(ws->in.maskv));
   std::memcpy(ws->in.st, state, sizeof(ws->in.st));

@@ -18,10 +18,12 @@ sets = []
 for t in range(4):
     inp = ob.synth.make_inputs(spec, N, config, step=t)
     sets.append({k: torch.from_numpy(inp[k]).cuda() for k in F})
-g = capi.BatchedOSC(spec, N)
+kw = {}
+if os.environ.get('OSC_SCALING'): kw['scaling'] = int(os.environ['OSC_SCALING'])
+g = capi.BatchedOSC(spec, N, capi.default_settings(**kw))
 def bind(t):
     g.bind_device_inputs(*[sets[t % 4][k].data_ptr() for k in F])
-for mode in ("condensed", "reference-parity"):
+for mode in ("reference-parity", "condensed"):
     bind(0)
     if mode == "condensed":
         g.reset_condensed(); step = g.step_condensed

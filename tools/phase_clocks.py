@@ -17,7 +17,7 @@ def build():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "libosc_b200_phase.so")
     src = os.path.join(g.PKG, "csrc", "osc_b200.cu")
-    deps = [src] + [os.path.join(g.PKG, "csrc", f) for f in ("osc_core.cuh", "osc_core3.cuh", "osc_warp.cuh")]
+    deps = [src] + [os.path.join(g.PKG, "csrc", f) for f in ("osc_core.cuh", "osc_core3.cuh", "osc_condensed.cuh", "osc_warp.cuh")]
     if g._newer(lib, deps):
         subprocess.run(["nvcc", *g.NVCC_FLAGS, "-DOSC_PHASE_CLOCKS", "-o", lib, src], check=True)
     return lib
@@ -40,7 +40,7 @@ def main():
     steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(3)]
     g = capi.BatchedOSC(spec, N)
     g.enable_timing(True)
-    buf = (C.c_ulonglong * 24)()
+    buf = (C.c_ulonglong * 32)()
 
     def report(tag):
         L.osc_debug_phase_clocks(buf, 1)
@@ -61,6 +61,24 @@ def main():
         it = r["iters"].mean()
         print(f"  cycles per iteration               {d(5, 4) / it:10.0f}")
 
+    if "--condensed" in sys.argv:
+        def creport(tag):
+            L.osc_debug_phase_clocks(buf, 1)
+            t = np.array(list(buf), dtype=np.uint64).astype(np.int64)
+            d = lambda a, b: float(np.int64(t[a] - t[b])) / N
+            r = g.results(); kt = g.read_timing()
+            print(f"--- condensed {tag}: kernel {kt.solve_ms:.3f} ms, iters mean {r['iters'].mean():.1f}")
+            for k, v in [("condense (Cholesky, G, d0, v)", d(18, 17)), ("P' rows (all passes)", d(20, 19)),
+                         ("Ruiz + assemble + warm start", d(22, 21)), ("set_rho + factor (K^-1)", d(24, 23)),
+                         ("admm (iterations + checks)", d(25, 24)), ("  iterations only", d(28, 27)),
+                         ("outputs", d(26, 25)), ("environment total", d(26, 17))]:
+                print(f"  {k:34s} {v:10.0f} cycles/env")
+            print(f"  cycles per iteration               {d(28, 27) / r['iters'].mean():10.0f}")
+        g.upload(steps[0]); g.step_condensed(); g.sync(); L.osc_debug_phase_clocks(buf, 1)
+        g.reset_condensed(); g.step_condensed(); g.sync(); creport("cold")
+        for rep in range(2):
+            g.upload(steps[1 + rep % 2]); g.step_condensed(); g.sync(); creport("warm")
+        return
     g.setup(steps[0]); g.step_device(); g.sync(); L.osc_debug_phase_clocks(buf, 1)
     g.setup(steps[0]); g.step_device(); g.sync(); report("cold")
     for rep in range(2):
