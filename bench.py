@@ -81,6 +81,22 @@ def algorithmic_flops_per_solve(spec, iters, check_every=25):
     return float(setup + per_iter * iters.mean() + per_check * np.ceil(iters / check_every).mean())
 
 
+def condensed_flops_per_solve(spec, iters, check_every=25):
+    """Algorithmic operation count of the condensed fast mode (n' = nu + 3 nc variables):
+    Cholesky of M, G = M^-1 [B Jc | -C], Hd G, the symmetric P' = G' Hd G, an n' x n' SPD
+    inverse, then per iteration one n' x n' mat-vec + friction rows + vector updates and per
+    check P'x through G and Hd."""
+    nv, nc = spec.nv, spec.nc
+    n1 = spec.nu + 3 * nc
+    m1 = 4 * nc + n1
+    iters = np.asarray(iters, dtype=np.float64)
+    setup = nv ** 3 / 3.0 + 2 * nv * nv * (n1 + 1) + 2 * nv * nv * n1 + nv * n1 * (n1 + 1) + n1 ** 3
+    scaling = 10 * 2 * (n1 * n1 + 2 * (12 * nc + n1))
+    per_iter = 2 * n1 * n1 + 2 * 2 * 12 * nc + 12 * m1
+    per_check = 2 * (2 * nv * n1) + 2 * nv * nv + 2 * 2 * 12 * nc
+    return float(setup + scaling + per_iter * iters.mean() + per_check * np.ceil(iters / check_every).mean())
+
+
 def scale_ops_per_solve(spec, passes=10):
     """Equilibration kernel (OSQP scale_data): every pass takes the infinity norm of every
     column and row of the scaled [P A'; A 0], i.e. one multiply and one compare per stored
@@ -184,7 +200,7 @@ def device_peak_dfma(capi, local, cache={}):
 
 
 def measure_resident(ob, capi, sharding, torch, spec, wl, n_envs, steps, warmup, nsets, rank,
-                     world, local, dev, hbm_peak, with_dual=False):
+                     world, local, dev, hbm_peak, with_dual=False, mode="reference"):
     """Device-resident warm-step throughput of one (robot, config, batch size) point: the same
     protocol as the headline (inputs in HBM, `nsets` resident control ticks cycling, CUDA
     events on the launch stream, max over ranks), plus the per-kernel roofline fractions."""
@@ -207,17 +223,22 @@ def measure_resident(ob, capi, sharding, torch, spec, wl, n_envs, steps, warmup,
         torch.cuda.synchronize()
 
     bind(0)
-    osc.setup(stream=stream)
+    if mode == "condensed":
+        osc.reset_condensed(stream)
+        step = osc.step_condensed
+    else:
+        osc.setup(stream=stream)
+        step = osc.step_device
     for t in range(warmup):
         bind(t)
-        osc.step_device(stream)
+        step(stream)
     osc.enable_timing(True)
     barrier()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     evs[0].record()
     for i, t in enumerate(range(warmup, warmup + steps)):
         bind(t)
-        osc.step_device(stream)
+        step(stream)
         evs[i + 1].record()
     barrier()
     ms = sharding.max_over_ranks(evs[0].elapsed_time(evs[-1]), dev) / steps
@@ -227,6 +248,18 @@ def measure_resident(ob, capi, sharding, torch, spec, wl, n_envs, steps, warmup,
     osc.enable_timing(False)
     res = osc.results(stream)
     dfma = device_peak_dfma(capi, local)
+    if mode == "condensed":
+        flops = condensed_flops_per_solve(spec, res["iters"]) * n_envs
+        return {"robot": spec.robot, "preset": wl["preset"], "synthetic_config": wl["config"],
+                "envs_per_gpu": n_envs, "total_envs": world * n_envs, "steps": steps,
+                "value": world * n_envs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                "iters_mean": float(res["iters"].mean()),
+                "solved_frac": float((res["status"] == capi.SOLVED).mean()),
+                "kernel_ms": {"build_qp_kernel": kt.build_ms, "condensed_kernel": kt.solve_ms},
+                "roofline": {"kernel": "condensed_kernel", "bound": "fp64_fma",
+                             "achieved": flops / (kt.solve_ms * 1e-3) / 1e12, "peak": dfma,
+                             "unit": "TFLOP/s", "frac": flops / (kt.solve_ms * 1e-3) / 1e12 / dfma,
+                             "algorithmic_flops_per_solve": flops / n_envs}}
     flops = algorithmic_flops_per_solve(spec, res["iters"]) * n_envs
     out = {"robot": spec.robot, "preset": wl["preset"], "synthetic_config": wl["config"],
            "envs_per_gpu": n_envs, "total_envs": world * n_envs, "steps": steps,
@@ -289,6 +322,88 @@ def one_robot_latency(ob, capi, spec, wl, local, reps=300):
             "value": 1e6 / float(np.median(lat)), "unit": UNIT,
             "iters": int(r["iters"][0]), "note": "wall clock per control step: pinned host buffers "
             "in, 3 kernels, torque back to the host (osc_step_host, few-robot path)"}
+
+
+def e2e_device_kinematics(ob, capi, sharding, torch, spec, wl, n_envs, steps, warmup, rank, world,
+                          local, dev):
+    """End to end with the MuJoCo-derived record made ON the device (osc_kinematics, SURVEY.md
+    8f rank 2): per step the host hands over qpos, qvel, targets and the contact mask from
+    pinned memory (0.4 kB per environment instead of the 13.4 kB OSCData record), the device
+    computes M, C, J, bias for a SYNTHETIC tree of the robot's topology (the real MJCF models
+    are external to the reference), runs the control step and returns the torques.  A
+    different input distribution than the headline workload (M, J follow from the tree, not
+    from the N(0, 0.3) generator): reported beside `e2e`, never instead of it."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))  # model builder only (host-side constants)
+    import osc_kinematics as okin
+    tree = okin.walter_like_tree(0) if spec.nv == 14 else okin.go2_like_tree(0)
+    model = capi.kin_model(tree)
+    stream = torch.cuda.current_stream().cuda_stream
+    sets = []
+    for t in range(NSETS):
+        qpos, qvel = okin.random_state(tree, n_envs, seed=t, first_env=rank * n_envs)
+        inp = ob.synth.make_inputs(spec, 256, wl["config"], step=t)  # targets / mask pattern
+        reps = (n_envs + 255) // 256
+        tg = np.tile(inp["targets"], (reps, 1, 1))[:n_envs] * 0.02  # scaled to the tree's masses
+        mk = np.tile(inp["mask"], (reps, 1))[:n_envs]
+        pin = {}
+        for k, a in (("qpos", qpos), ("qvel", qvel), ("targets", tg), ("mask", mk)):
+            p = capi.pinned_empty(a.shape)
+            p[...] = a
+            pin[k] = p
+        sets.append(pin)
+    dq = torch.empty((n_envs, tree.nq), dtype=torch.float64, device=dev)
+    dv = torch.empty((n_envs, tree.nv), dtype=torch.float64, device=dev)
+    osc = capi.BatchedOSC(spec, n_envs, device=local)
+    buf = osc.device_buffers()
+    tq = capi.pinned_empty((n_envs, spec.nu))
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    H2D, D2H = 1, 2
+
+    def copy(dst, src, nbytes, kind):
+        rc = rt.cudaMemcpyAsync(ctypes.c_void_p(dst), ctypes.c_void_p(src), ctypes.c_size_t(nbytes),
+                                kind, ctypes.c_void_p(stream))
+        assert rc == 0, rc
+
+    def one(t, first=False):
+        s = sets[t % NSETS]
+        copy(dq.data_ptr(), s["qpos"].ctypes.data, s["qpos"].nbytes, H2D)
+        copy(dv.data_ptr(), s["qvel"].ctypes.data, s["qvel"].nbytes, H2D)
+        copy(buf.targets, s["targets"].ctypes.data, s["targets"].nbytes, H2D)
+        copy(buf.mask, s["mask"].ctypes.data, s["mask"].nbytes, H2D)
+        osc.kinematics(model, dq.data_ptr(), dv.data_ptr(), stream)
+        if first:
+            osc.setup(stream=stream)
+        osc.step_device(stream)
+        copy(tq.ctypes.data, buf.torque, tq.nbytes, D2H)
+        osc.sync(stream)
+
+    one(0, first=True)
+    for t in range(warmup):
+        one(t)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for t in range(warmup, warmup + steps):
+        one(t)
+    g1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms = sharding.max_over_ranks(g0.elapsed_time(g1), dev) / steps
+    r = osc.results(stream)
+    h2d = sum(sets[0][k].nbytes for k in ("qpos", "qvel", "targets", "mask"))
+    out = {"value": world * n_envs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": tq.nbytes,
+           "iters_mean": float(r["iters"].mean()),
+           "solved_frac": float((r["status"] == capi.SOLVED).mean()),
+           "torques_finite": bool(np.isfinite(tq).all()),
+           "inputs": "qpos, qvel, targets, mask from pinned host memory; M, C, J, bias computed on "
+                     "the device for a synthetic tree of the robot's topology (osc_kinematics)"}
+    osc.close()
+    return out
 
 
 def cpu_leg(spec, wl, sample_envs, steps, warmup, n_threads=0):
@@ -573,6 +688,19 @@ def main():
         for n in (1024, 4096, 65536, 131072):  # 16384 per GPU is the headline itself
             sweep.append(mr(DEFAULT_WORKLOAD, n, 2 if n > 16384 else NSETS))
         configs["C5_walter_sr_sweep_per_gpu"] = sweep
+        # the condensed fast mode (north_star subsystems (1)/(2)), reported separately: same
+        # QP, same OSQP tolerances, different iterates -- never the reference-parity path
+        fast = {"mode": "condensed (osc_step_condensed): Cholesky of M, G = M^-1 [B Jc], QP in "
+                        "(u, z) only; parity = its own oracle (oracle/osc_condensed.py), "
+                        "tests/test_gpu_parity.py::test_condensed_*"}
+        for key, name, n in (("walter_sr_tumbling_16384_per_gpu", DEFAULT_WORKLOAD, 16384),
+                             ("go2_standing_4096", "go2_standing_4096", 4096)):
+            r = mr(name, n, NSETS, mode="condensed")
+            fast[key] = r
+        configs["fast_mode_condensed"] = fast
+        configs["e2e_device_kinematics_walter_sr_16384_per_gpu"] = e2e_device_kinematics(
+            ob, capi, sharding, torch, ob.load_preset(WORKLOADS[DEFAULT_WORKLOAD]["preset"]),
+            WORKLOADS[DEFAULT_WORKLOAD], 16384, ksteps, args.warmup, rank, world, local, dev)
         if world == 1:
             wl1 = WORKLOADS["walter_sr_standing_4096"]
             configs["C1_walter_sr_standing_one_robot"] = one_robot_latency(

@@ -258,6 +258,35 @@ int osc_contact_mask_from_contacts(osc_handle *h, const int *geom_pairs, const i
                                    int max_con, const int *contact_geom_ids,
                                    const int *site_of_geom, void *stream);
 
+/* ---- the step before THAT: the MuJoCo-derived record on the device.
+ * update_mj_data / update_osc_data (operational_space_controller.h:394-513) for a floating-base
+ * tree of hinge joints, from qpos / qvel and a host-supplied model: M (mj_fullM, :436-438),
+ * C (qfrc_bias, :441-442), J = [jacp; jacr] per task site (mj_jac, :459-487) and
+ * bias = Jdot qvel (mj_jacDot, :491-492) are written into the handle's OWN M, C, J, bias input
+ * buffers in the OSCData layouts, so that 13.4 kB per environment and step never cross PCIe.
+ * MuJoCo conventions: qpos = [base xyz, base quat (w x y z), hinge angles], qvel = [world-frame
+ * base linear velocity, BODY-frame base angular velocity, hinge rates]; body b >= 1 hangs off
+ * parent[b] < b through one hinge about jaxis[b] anchored at its own origin.  The robots' MJCF
+ * files are external to the reference (not in this repository): the model numbers are the
+ * caller's; oracle/osc_kinematics.py is the CPU restatement this is tested against. */
+#define OSC_KIN_MAX_BODIES 16
+typedef struct {
+  int nb, ns;                            /* bodies (nv = 6 + nb - 1), task sites (= spec.ns) */
+  int parent[OSC_KIN_MAX_BODIES];        /* parent[0] = -1 */
+  double bpos[OSC_KIN_MAX_BODIES][3];    /* body origin in the parent frame */
+  double bquat[OSC_KIN_MAX_BODIES][4];   /* body orientation in the parent frame at zero angle */
+  double jaxis[OSC_KIN_MAX_BODIES][3];   /* hinge axis, body frame, unit length */
+  double mass[OSC_KIN_MAX_BODIES];
+  double ipos[OSC_KIN_MAX_BODIES][3];    /* centre of mass, body frame */
+  double inertia[OSC_KIN_MAX_BODIES][6]; /* about the centre of mass, body frame: xx yy zz xy xz yz */
+  int site_body[OSC_MAX_SITES];
+  double site_pos[OSC_MAX_SITES][3];     /* body frame; site order = the controller's site_list */
+  double gravity[3];
+} osc_kin_model;
+/* qpos [n_envs][nv + 1], qvel [n_envs][nv]: DEVICE pointers. */
+int osc_kinematics(osc_handle *h, const osc_kin_model *model, const double *qpos,
+                   const double *qvel, void *stream);
+
 /* How many environment-steps so far took the reference's sparsity-change path
  * (update_optimization :571-584: UpdateObjectiveAndConstraintMatrices rejected the new
  * pattern -> solver re-Init with rho reset + SetWarmStart(solution, dual_solution)).

@@ -52,6 +52,7 @@ __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 
 #include "osc_params.h"
 #include "osc_condensed.cuh"
+#include "osc_kinematics.cuh"
 
 namespace osc {
 
@@ -1056,6 +1057,23 @@ int launch_condensed(osc_handle* h, cudaStream_t st, int n) {
   }
 }
 
+// ---- device-side kinematics / dynamics (the step before the hot path) ------------------------
+template <class D>
+int launch_kinematics(osc_handle* h, const osc_kin_model* m, const double* qpos,
+                             const double* qvel, cudaStream_t st) {
+  const size_t smem = osc::kKinWarps * sizeof(osc::KinWorkspace<D>);
+  auto kern = osc::kinematics_kernel<D>;
+  OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (h->n_envs + osc::kKinWarps - 1) / osc::kKinWarps;
+  if (grid > h->sm_count * 2) grid = h->sm_count * 2;
+  kern<<<grid, osc::kKinWarps * 32, smem, st>>>(*m, qpos, qvel, h->dM, h->dC, h->dJ, h->dBias,
+                                               h->n_envs);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
+
 #define OSC_DISPATCH(h, fn, ...)                                                    \
   ((h)->shape == osc::Shape::kWalter ? fn<osc::WalterDims>(__VA_ARGS__)             \
                                      : fn<osc::Go2Dims>(__VA_ARGS__))
@@ -1816,6 +1834,38 @@ int osc_gather_buffers(osc_handle* h, double** torque_all, double** stats_all) {
   if (torque_all) *torque_all = h->g_slab;
   if (stats_all) *stats_all = h->g_slab + (size_t)h->g_world * h->n_envs * h->nu;
   return OSC_OK;
+}
+
+int osc_kinematics(osc_handle* h, const osc_kin_model* model, const double* qpos,
+                   const double* qvel, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!model || !qpos || !qvel) {
+    h->err = "osc_kinematics: null argument";
+    return OSC_ERR_INVALID;
+  }
+  if (model->nb < 1 || model->nb > OSC_KIN_MAX_BODIES || 6 + model->nb - 1 != h->nv ||
+      model->ns != h->ns || model->parent[0] != -1) {
+    h->err = "osc_kinematics: model does not match the robot shape (nv = 6 + nb - 1, ns)";
+    return OSC_ERR_INVALID;
+  }
+  for (int b = 1; b < model->nb; ++b)
+    if (model->parent[b] < 0 || model->parent[b] >= b) {
+      h->err = "osc_kinematics: bodies must be in topological order (parent[b] < b)";
+      return OSC_ERR_INVALID;
+    }
+  for (int s = 0; s < model->ns; ++s)
+    if (model->site_body[s] < 0 || model->site_body[s] >= model->nb) {
+      h->err = "osc_kinematics: site_body out of range";
+      return OSC_ERR_INVALID;
+    }
+  if (h->iM != h->dM || h->iC != h->dC || h->iJ != h->dJ || h->iBias != h->dBias) {
+    h->err = "osc_kinematics: M, C, J or bias is bound to caller-owned memory";
+    return OSC_ERR_STATE;
+  }
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  return h->shape == osc::Shape::kWalter
+             ? launch_kinematics<osc::WalterDims>(h, model, qpos, qvel, (cudaStream_t)stream)
+             : launch_kinematics<osc::Go2Dims>(h, model, qpos, qvel, (cudaStream_t)stream);
 }
 
 long long osc_kernel_launches(const osc_handle* h) { return h ? h->launches : 0; }

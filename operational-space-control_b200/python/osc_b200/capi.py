@@ -30,8 +30,9 @@ EXPORTS = (
     "osc_targets_pd", "osc_contact_mask_from_contacts", "osc_host_traffic",
     "osc_selftest_warp",
     "osc_gather_create", "osc_gather_attach", "osc_gather_torques", "osc_gather_buffers",
-    "osc_step_condensed", "osc_reset_condensed",
+    "osc_step_condensed", "osc_reset_condensed", "osc_kinematics",
 )
+KIN_MAX_BODIES = 16
 IPC_HANDLE_BYTES = 64
 GATHER_STATS = 8
 GATHER_STAT_NAMES = ("n_envs", "solved", "iters_sum", "iters_max", "pri_res_max", "dua_res_max",
@@ -76,6 +77,41 @@ class CDeviceBuffers(C.Structure):
 class CSiteState(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in (
         "pos", "quat", "vel", "angvel", "pos_des", "quat_des", "vel_des", "angvel_des")]
+
+
+class CKinModel(C.Structure):
+    _fields_ = [("nb", C.c_int), ("ns", C.c_int), ("parent", C.c_int * 16),
+                ("bpos", (C.c_double * 3) * 16), ("bquat", (C.c_double * 4) * 16),
+                ("jaxis", (C.c_double * 3) * 16), ("mass", C.c_double * 16),
+                ("ipos", (C.c_double * 3) * 16), ("inertia", (C.c_double * 6) * 16),
+                ("site_body", C.c_int * 32), ("site_pos", (C.c_double * 3) * 32),
+                ("gravity", C.c_double * 3)]
+
+
+def kin_model(tree, gravity=(0.0, 0.0, -9.81)) -> CKinModel:
+    """osc_kin_model from a tree description with the attributes of oracle/osc_kinematics.Tree
+    (parent, bpos, bquat, jaxis, mass, ipos, inertia [nb,3,3], site_body, site_pos)."""
+    m = CKinModel()
+    m.nb, m.ns = int(tree.nb), int(tree.ns)
+    for b in range(tree.nb):
+        m.parent[b] = int(tree.parent[b])
+        m.mass[b] = float(tree.mass[b])
+        for k in range(3):
+            m.bpos[b][k] = float(tree.bpos[b][k])
+            m.jaxis[b][k] = float(tree.jaxis[b][k])
+            m.ipos[b][k] = float(tree.ipos[b][k])
+        for k in range(4):
+            m.bquat[b][k] = float(tree.bquat[b][k])
+        I = tree.inertia[b]
+        for k, v in enumerate((I[0][0], I[1][1], I[2][2], I[0][1], I[0][2], I[1][2])):
+            m.inertia[b][k] = float(v)
+    for s in range(tree.ns):
+        m.site_body[s] = int(tree.site_body[s])
+        for k in range(3):
+            m.site_pos[s][k] = float(tree.site_pos[s][k])
+    for k in range(3):
+        m.gravity[k] = float(gravity[k])
+    return m
 
 
 class CKernelTimes(C.Structure):
@@ -130,6 +166,7 @@ def load():
     L.osc_gather_attach.argtypes = [vp, vp, C.POINTER(vp)]
     L.osc_gather_torques.argtypes = [vp, vp]
     L.osc_gather_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.osc_kinematics.argtypes = [vp, C.POINTER(CKinModel), vp, vp, vp]
     L.osc_step_condensed.argtypes = [vp, vp]
     L.osc_reset_condensed.argtypes = [vp, vp]
     L.osc_timing_enable.argtypes = [vp, C.c_int]
@@ -263,6 +300,12 @@ class BatchedOSC:
         """Hot-loop variant of step(): pre-resolved input pointers, caller-owned output."""
         self._check(self.L.osc_step_host(self.h, *ptrs, torque_out.ctypes.data, stream),
                     "osc_step_host")
+
+    def kinematics(self, model: CKinModel, qpos_dev: int, qvel_dev: int, stream=None):
+        """M, C, J, bias of every environment from qpos / qvel (DEVICE pointers) into the
+        handle's own input buffers (update_mj_data / update_osc_data on the device)."""
+        self._check(self.L.osc_kinematics(self.h, C.byref(model), qpos_dev, qvel_dev, stream),
+                    "osc_kinematics")
 
     def step_condensed(self, stream=None):
         """Control step of the CONDENSED fast mode on the inputs resident in HBM (Cholesky of

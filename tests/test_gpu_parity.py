@@ -928,3 +928,70 @@ def test_condensed_and_reference_paths_agree_at_the_optimum(oracle):
     # objective values agree; the torques themselves sit in a flat valley of that objective
     # (cond(H) ~ 5e6: reported above, not gated)
     assert rel.max() < 1e-7
+
+
+@pytest.mark.parametrize("which,preset,config", [("walter", "walter_sr_true_tumbling_mjjoint", "tumbling"),
+                                                 ("go2", "unitree_go2", "go2_standing")])
+def test_device_kinematics_match_the_numpy_restatement(oracle, which, preset, config):
+    """osc_kinematics (update_mj_data / update_osc_data on the device)
+    against oracle/osc_kinematics.py on a synthetic tree of the robot's topology: M, C, J, bias
+    to FP64 round-off in the OSCData layouts; then a control step on the device-made record
+    equals the step on the same record uploaded from the host, and matches the oracle."""
+    import torch
+    import osc_b200 as ob
+    import osc_kinematics as okin
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    tree = okin.walter_like_tree(2) if which == "walter" else okin.go2_like_tree(2)
+    assert tree.nv == spec.nv and tree.ns == spec.ns
+    n_envs = 333
+    qpos, qvel = okin.random_state(tree, n_envs, seed=9)
+    M, C, J, bias = okin.osc_data_batch(tree, qpos, qvel)
+    base = ob.synth.make_inputs(spec, n_envs, config)
+    g = capi.BatchedOSC(spec, n_envs)
+    g.upload(dict(base, M=M * 0, C=C * 0, J=J * 0, bias=bias * 0))   # targets / mask from the host
+    dq, dv = torch.from_numpy(qpos).cuda(), torch.from_numpy(qvel).cuda()
+    g.kinematics(capi.kin_model(tree), dq.data_ptr(), dv.data_ptr())
+    g.sync()
+    buf = g.device_buffers()
+    import ctypes as Ct
+    rt = Ct.CDLL("libcudart.so.12")
+
+    def read(ptr, shape):
+        out = np.empty(shape)
+        assert rt.cudaMemcpy(Ct.c_void_p(out.ctypes.data), Ct.c_void_p(ptr), Ct.c_size_t(out.nbytes), 2) == 0
+        return out
+
+    Md, Cd = read(buf.M, M.shape), read(buf.C, C.shape)
+    Jd, bd = read(buf.J, J.shape), read(buf.bias, bias.shape)
+    sc = lambda a: 1e-12 * (1.0 + np.abs(a).max())  # noqa: E731
+    np.testing.assert_allclose(Jd, J, rtol=0, atol=sc(J))
+    np.testing.assert_allclose(Md, M, rtol=0, atol=sc(M))
+    np.testing.assert_allclose(Cd, C, rtol=0, atol=sc(C))
+    np.testing.assert_allclose(bd, bias, rtol=0, atol=sc(bias))
+    assert np.array_equal(Md, Md.transpose(0, 2, 1)) or np.abs(Md - Md.transpose(0, 2, 1)).max() < sc(M)
+    # structural zeros are exact zeros (they decide OSQP's sparsity pattern, :558-584)
+    assert np.array_equal(Jd == 0.0, J == 0.0)
+    # control step on the device-made record == on the same record from the host; == oracle
+    g.setup()
+    g.step_device()
+    a = g.results()
+    inp = dict(base, M=Md, C=Cd, J=Jd, bias=bd)
+    g2 = capi.BatchedOSC(spec, n_envs)
+    g2.setup(inp)
+    g2.step_device()
+    b = g2.results()
+    assert np.array_equal(a["torque"], b["torque"]) and np.array_equal(a["iters"], b["iters"])
+    ref = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    ref.setup(inp)
+    o = ref.step(inp)
+    keep = o["margin"] > 1e-6
+    assert keep.mean() > 0.97
+    assert np.array_equal(a["iters"][keep], o["iters"][keep])
+    d = np.abs(a["torque"] - o["torque"])[keep]
+    tol = (ATOL + RTOL * np.abs(o["torque"]))[keep]
+    assert (d <= tol).mean() > 0.99, (d / tol).max()
+    with pytest.raises(capi.OscError):
+        bad = capi.kin_model(tree)
+        bad.ns = spec.ns + 1
+        g.kinematics(bad, dq.data_ptr(), dv.data_ptr())
