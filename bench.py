@@ -37,7 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "operational-space-control_b200", "python"
 # on stderr instead of being silenced.
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
-os.environ.setdefault("NCCL_DEBUG", "INFO")
+os.environ["NCCL_DEBUG"] = os.environ.get("OSC_BENCH_NCCL_DEBUG", "INFO")
 os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
 
 

@@ -245,6 +245,26 @@ int osc_targets_pd(osc_handle *h, const osc_site_state *s, const double *kp_lin,
                    const double *kd_lin, const double *kp_ang, const double *kd_ang,
                    void *stream);
 
+/* The Walter tumbling driver's own target laws (examples/walter_sr_true_tumbling_mjjoint.cc,
+ * BASELINE.json configs[2]) for every environment, into the handle's `targets` input:
+ *   rows 1-4, shins (:695-802):  alpha_y = shin_kp ((th0 + shin_rate t) - th) + shin_kv (shin_rate - (th - th_prev)/dt)
+ *   rows 5-8, thighs (:873-973): a_z = thigh_kp ((z0 + thigh_height_offset) - z) + thigh_kv (thigh_rate - (z - z_prev)/dt)
+ *   row 0, torso (:1001-1019): every gain is zero in that driver -> zeros; contact rows: zeros.
+ * shin_* / thigh_*: DEVICE arrays [n_envs][4] in the driver's leg order (tl, tr, hl, hr):
+ * joint angle (qpos[jnt_qposadr[2,4,6,8]]) / thigh site height (site_xpos z), their values at the
+ * previous control step and at t = 0.  Only the Walter shapes (ns = 17). */
+typedef struct {
+  double shin_kp, shin_kv, shin_rate;       /* 2400, 2400, 4 rad/s */
+  double thigh_kp, thigh_kv, thigh_rate;    /* 2000, 300, 0 */
+  double thigh_height_offset;               /* -0.025 m */
+} osc_walter_tumbling_gains;
+int osc_walter_tumbling_default_gains(osc_walter_tumbling_gains *g);
+int osc_targets_walter_tumbling(osc_handle *h, const osc_walter_tumbling_gains *g,
+                                const double *shin_angle, const double *shin_angle_prev,
+                                const double *shin_angle0, const double *thigh_z,
+                                const double *thigh_z_prev, const double *thigh_z0, double time,
+                                double dt, void *stream);
+
 /* Contact mask from MuJoCo contact pairs (walter_sr_true_tumbling_mjjoint.cc:523-558):
  * every contact k < ncon[e] whose geom[0] or geom[1] is a listed id (`wheel_sites_mujoco`,
  * :436) contributes the first site on that geom's body (getSiteIdsOnSameBodyAsGeom, :106);

@@ -654,6 +654,33 @@ targets_pd_kernel(const __grid_constant__ PdGains g, const double* __restrict__ 
   }
 }
 
+// examples/walter_sr_true_tumbling_mjjoint.cc:695-802, 873-973, 1001-1019: the tumbling
+// driver's target laws, one thread per (environment, site row)
+__global__ void __launch_bounds__(256)
+targets_walter_tumbling_kernel(const osc_walter_tumbling_gains g, const double* __restrict__ sa,
+                               const double* __restrict__ sp, const double* __restrict__ s0,
+                               const double* __restrict__ tz, const double* __restrict__ tp,
+                               const double* __restrict__ t0, double time, double inv_dt,
+                               double* __restrict__ targets, int ns, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i / ns;
+    const int row = (int)(i - e * ns);
+    double t[6] = {0, 0, 0, 0, 0, 0};
+    if (row >= 1 && row <= 4) {
+      const long long k = 4 * e + (row - 1);
+      const double vel = (sa[k] - sp[k]) * inv_dt;
+      t[4] = g.shin_kp * ((s0[k] + g.shin_rate * time) - sa[k]) + g.shin_kv * (g.shin_rate - vel);
+    } else if (row >= 5 && row <= 8) {
+      const long long k = 4 * e + (row - 5);
+      const double vel = (tz[k] - tp[k]) * inv_dt;
+      t[2] = g.thigh_kp * ((t0[k] - 0.0 + g.thigh_height_offset) - tz[k]) + g.thigh_kv * (g.thigh_rate - vel);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) targets[6 * i + c] = t[c];
+  }
+}
+
 struct ContactIds {
   int id[kMaxNu];         // nc <= 16 listed geoms
   unsigned bits[kMaxNu];  // mask entries a contact on listed geom j raises
@@ -700,7 +727,8 @@ struct GatherArgs {
   double step;
 };
 
-__global__ void __launch_bounds__(256) gather_push_kernel(const __grid_constant__ GatherArgs a) {
+constexpr int kGatherThreads = 1024;
+__global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const __grid_constant__ GatherArgs a) {
   if (blockIdx.x == 0) {
     // statistics of this rank
     double cnt = 0, solved = 0, isum = 0, imax = 0, pmax = 0, dmax = 0;
@@ -715,7 +743,7 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const __grid_constant_
       pmax = pr > pmax ? pr : pmax;
       dmax = du > dmax ? du : dmax;
     }
-    __shared__ double red[6][8];
+    __shared__ double red[6][kGatherThreads / 32];
     double v[6] = {cnt, solved, isum, imax, pmax, dmax};
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
@@ -730,7 +758,7 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const __grid_constant_
       double r = 0.0;
       const int q = threadIdx.x;
       if (q < 6) {
-        for (int w = 0; w < 8; ++w) r = q < 3 ? r + red[q][w] : (red[q][w] > r ? red[q][w] : r);
+        for (int w = 0; w < kGatherThreads / 32; ++w) r = q < 3 ? r + red[q][w] : (red[q][w] > r ? red[q][w] : r);
       } else if (q == 6) {
         r = (double)*a.reinits;
       } else {
@@ -1689,6 +1717,47 @@ int osc_targets_pd(osc_handle* h, const osc_site_state* s, const double* kp_lin,
   return OSC_OK;
 }
 
+int osc_walter_tumbling_default_gains(osc_walter_tumbling_gains* g) {
+  if (!g) return OSC_ERR_INVALID;
+  g->shin_kp = 800.0 * 3.0; g->shin_kv = 800.0 * 3.0; g->shin_rate = 0.1 * 8.0 * 5.0;
+  g->thigh_kp = 4000.0 * 0.5; g->thigh_kv = 600.0 * 0.5; g->thigh_rate = 0.0;
+  g->thigh_height_offset = -0.025;
+  return OSC_OK;
+}
+
+int osc_targets_walter_tumbling(osc_handle* h, const osc_walter_tumbling_gains* g,
+                                const double* shin_angle, const double* shin_angle_prev,
+                                const double* shin_angle0, const double* thigh_z,
+                                const double* thigh_z_prev, const double* thigh_z0, double time,
+                                double dt, void* stream) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  if (!shin_angle || !shin_angle_prev || !shin_angle0 || !thigh_z || !thigh_z_prev || !thigh_z0 ||
+      !(dt > 0.0)) {
+    h->err = "osc_targets_walter_tumbling: null argument or dt <= 0";
+    return OSC_ERR_INVALID;
+  }
+  if (h->ns != 17) {
+    h->err = "osc_targets_walter_tumbling: the Walter site list (17 sites) only";
+    return OSC_ERR_INVALID;
+  }
+  if (h->iTargets != h->dTargets) {
+    h->err = "osc_targets_walter_tumbling: the targets input is bound to caller-owned memory";
+    return OSC_ERR_STATE;
+  }
+  osc_walter_tumbling_gains gg;
+  if (g) gg = *g; else osc_walter_tumbling_default_gains(&gg);
+  OSC_CUDA(h, cudaSetDevice(h->device));
+  const long long total = (long long)h->n_envs * h->ns;
+  int grid = (int)((total + 255) / 256);
+  if (grid > h->sm_count * 16) grid = h->sm_count * 16;
+  osc::targets_walter_tumbling_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      gg, shin_angle, shin_angle_prev, shin_angle0, thigh_z, thigh_z_prev, thigh_z0, time, 1.0 / dt,
+      h->dTargets, h->ns, total);
+  OSC_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return OSC_OK;
+}
+
 int osc_contact_mask_from_contacts(osc_handle* h, const int* geom_pairs, const int* ncon,
                                    int max_con, const int* contact_geom_ids,
                                    const int* site_of_geom, void* stream) {
@@ -1817,9 +1886,9 @@ int osc_gather_torques(osc_handle* h, void* stream) {
   a.rank = h->g_rank; a.world = h->g_world; a.n_envs = h->n_envs;
   a.step = (double)(++h->g_steps);
   const size_t pairs = a.slice / 2;
-  int grid = (int)((pairs + 255) / 256);
-  if (grid > h->sm_count * 4) grid = h->sm_count * 4;
-  osc::gather_push_kernel<<<grid + 1, 256, 0, (cudaStream_t)stream>>>(a);
+  int grid = (int)((pairs + osc::kGatherThreads - 1) / osc::kGatherThreads);
+  if (grid > h->sm_count) grid = h->sm_count;
+  osc::gather_push_kernel<<<grid + 1, osc::kGatherThreads, 0, (cudaStream_t)stream>>>(a);
   OSC_CUDA(h, cudaGetLastError());
   h->launches++;
   return OSC_OK;

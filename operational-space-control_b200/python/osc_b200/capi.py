@@ -31,6 +31,7 @@ EXPORTS = (
     "osc_selftest_warp",
     "osc_gather_create", "osc_gather_attach", "osc_gather_torques", "osc_gather_buffers",
     "osc_step_condensed", "osc_reset_condensed", "osc_kinematics",
+    "osc_walter_tumbling_default_gains", "osc_targets_walter_tumbling",
 )
 KIN_MAX_BODIES = 16
 IPC_HANDLE_BYTES = 64
@@ -77,6 +78,11 @@ class CDeviceBuffers(C.Structure):
 class CSiteState(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in (
         "pos", "quat", "vel", "angvel", "pos_des", "quat_des", "vel_des", "angvel_des")]
+
+
+class CWalterTumblingGains(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("shin_kp", "shin_kv", "shin_rate", "thigh_kp",
+                                          "thigh_kv", "thigh_rate", "thigh_height_offset")]
 
 
 class CKinModel(C.Structure):
@@ -167,6 +173,9 @@ def load():
     L.osc_gather_torques.argtypes = [vp, vp]
     L.osc_gather_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.osc_kinematics.argtypes = [vp, C.POINTER(CKinModel), vp, vp, vp]
+    L.osc_walter_tumbling_default_gains.argtypes = [C.POINTER(CWalterTumblingGains)]
+    L.osc_targets_walter_tumbling.argtypes = [vp, C.POINTER(CWalterTumblingGains)] + [vp] * 6 + [
+        C.c_double, C.c_double, vp]
     L.osc_step_condensed.argtypes = [vp, vp]
     L.osc_reset_condensed.argtypes = [vp, vp]
     L.osc_timing_enable.argtypes = [vp, C.c_int]
@@ -371,6 +380,16 @@ class BatchedOSC:
         dp = C.POINTER(C.c_double)
         self._check(self.L.osc_targets_pd(self.h, C.byref(st), *[a.ctypes.data_as(dp) for a in g],
                                           stream), "osc_targets_pd")
+
+    def targets_walter_tumbling(self, shin_angle, shin_angle_prev, shin_angle0, thigh_z,
+                                thigh_z_prev, thigh_z0, time: float, dt: float, gains=None,
+                                stream=None):
+        """The Walter tumbling driver's target laws (walter_sr_true_tumbling_mjjoint.cc:695-1019)
+        from DEVICE arrays [n_envs, 4] into the handle's `targets` input."""
+        self._check(self.L.osc_targets_walter_tumbling(
+            self.h, C.byref(gains) if gains is not None else None, shin_angle, shin_angle_prev,
+            shin_angle0, thigh_z, thigh_z_prev, thigh_z0, float(time), float(dt), stream),
+            "osc_targets_walter_tumbling")
 
     def contact_mask_from_contacts(self, geom_pairs_dev: int, ncon_dev: int, max_con: int,
                                    contact_geom_ids, site_of_geom=None, stream=None):

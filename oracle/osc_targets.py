@@ -11,6 +11,8 @@ Follows (paths relative to /root/reference):
   examples/walter_sr_true_tumbling_mjjoint.cc:106    getSiteIdsOnSameBodyAsGeom()
   examples/walter_sr_true_tumbling_mjjoint.cc:152    getBinaryRepresentation_std_find()
   examples/walter_sr_true_tumbling_mjjoint.cc:523-558  contacts -> contact_mask
+  examples/walter_sr_true_tumbling_mjjoint.cc:695-802  shin rows 1-4 (alpha_y from the joint angle)
+  examples/walter_sr_true_tumbling_mjjoint.cc:873-973  thigh rows 5-8 (height law), row 0 (:1001-1019)
 """
 from __future__ import annotations
 
@@ -69,3 +71,29 @@ def contact_mask_from_contacts(geom_pairs, ncon, listed, site_of_geom=None):
         for c, s in enumerate(listed):
             mask[e, c] = 1.0 if s in sites else 0.0
     return mask
+
+
+# the numbers of examples/walter_sr_true_tumbling_mjjoint.cc (BASELINE.json configs[2])
+WALTER_TUMBLING = dict(shin_kp=800.0 * 3.0, shin_kv=800.0 * 3.0, shin_rate=0.1 * 8.0 * 5.0,
+                       thigh_kp=4000.0 * 0.5, thigh_kv=600.0 * 0.5, thigh_rate=0.0,
+                       thigh_height_offset=-0.025)
+
+
+def targets_walter_tumbling(shin_angle, shin_angle_prev, shin_angle0, thigh_z, thigh_z_prev,
+                            thigh_z0, time, dt, ns=17, **kw):
+    """walter_sr_true_tumbling_mjjoint.cc per environment.  Arrays [N, 4] in the driver's leg
+    order (tl, tr, hl, hr); returns targets [N, ns, 6]:
+      rows 1-4 (shins, :695-802):  (0,0,0, 0, kp (th0 + rate t - th) + kv (rate - (th - th_prev)/dt), 0)
+      rows 5-8 (thighs, :873-973): (0,0, kp ((z0 + offset) - z) + kv (rate_z - (z - z_prev)/dt), 0,0,0)
+      row 0 (torso, :1001-1019): all gains zero -> zeros; contact rows 9-16: never written."""
+    g = dict(WALTER_TUMBLING, **kw)
+    sa, sp, s0 = (np.asarray(a, float) for a in (shin_angle, shin_angle_prev, shin_angle0))
+    tz, tp, t0 = (np.asarray(a, float) for a in (thigh_z, thigh_z_prev, thigh_z0))
+    N = sa.shape[0]
+    out = np.zeros((N, ns, 6))
+    shin_vel = (sa - sp) / dt
+    out[:, 1:5, 4] = g["shin_kp"] * ((s0 + g["shin_rate"] * time) - sa) + g["shin_kv"] * (g["shin_rate"] - shin_vel)
+    thigh_vel = (tz - tp) / dt
+    out[:, 5:9, 2] = (g["thigh_kp"] * ((t0 - 0.0 + g["thigh_height_offset"]) - tz)
+                      + g["thigh_kv"] * (g["thigh_rate"] - thigh_vel))
+    return out

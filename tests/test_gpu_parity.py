@@ -995,3 +995,35 @@ def test_device_kinematics_match_the_numpy_restatement(oracle, which, preset, co
         bad = capi.kin_model(tree)
         bad.ns = spec.ns + 1
         g.kinematics(bad, dq.data_ptr(), dv.data_ptr())
+
+
+def test_walter_tumbling_target_laws_on_device():
+    """osc_targets_walter_tumbling (examples/walter_sr_true_tumbling_mjjoint.cc:695-1019) against
+    its numpy restatement: same arithmetic, 1e-12 relative; wrong shape is refused."""
+    import torch
+    import osc_b200 as ob
+    import osc_targets as ot
+    from osc_b200 import capi
+    spec = ob.load_preset("walter_sr_true_tumbling_mjjoint")
+    n_envs = 1000
+    rng = np.random.default_rng(11)
+    a = {k: rng.normal(0.0, 1.0, (n_envs, 4)) for k in ("sa", "s0", "tz", "t0")}
+    a["sp"] = a["sa"] - rng.normal(0.0, 0.01, (n_envs, 4))
+    a["tp"] = a["tz"] - rng.normal(0.0, 0.001, (n_envs, 4))
+    dev = {k: torch.from_numpy(v).cuda() for k, v in a.items()}
+    g = capi.BatchedOSC(spec, n_envs)
+    g.targets_walter_tumbling(dev["sa"].data_ptr(), dev["sp"].data_ptr(), dev["s0"].data_ptr(),
+                              dev["tz"].data_ptr(), dev["tp"].data_ptr(), dev["t0"].data_ptr(),
+                              time=1.25, dt=0.002)
+    g.sync()
+    want = ot.targets_walter_tumbling(a["sa"], a["sp"], a["s0"], a["tz"], a["tp"], a["t0"], 1.25, 0.002)
+    import ctypes as Ct
+    got = np.empty_like(want)
+    assert Ct.CDLL("libcudart.so.12").cudaMemcpy(Ct.c_void_p(got.ctypes.data),
+                                                 Ct.c_void_p(g.device_buffers().targets),
+                                                 Ct.c_size_t(got.nbytes), 2) == 0
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
+    go2 = capi.BatchedOSC(ob.load_preset("unitree_go2"), 8)
+    with pytest.raises(capi.OscError):
+        go2.targets_walter_tumbling(*[dev[k].data_ptr() for k in ("sa", "sp", "s0", "tz", "tp", "t0")],
+                                    time=0.0, dt=0.002)

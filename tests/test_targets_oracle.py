@@ -66,3 +66,22 @@ def test_contact_mask_by_hand():
     # a geom -> site table that is not the identity: geom 4's body carries site 3
     m2 = ot.contact_mask_from_contacts(pairs, ncon, listed, [3, 3, 7, 8, 11, 12, 15, 16])
     assert np.array_equal(m2[0], [1, 0, 0, 0, 1, 0, 0, 1])
+
+
+def test_walter_tumbling_laws_hand_worked():
+    """walter_sr_true_tumbling_mjjoint.cc:695-802 (shins), :873-973 (thighs): one environment by
+    hand with the driver's gains (2400 / 2400 / 4 rad/s; 2000 / 300; -0.025 m)."""
+    import osc_targets as ot
+    t = ot.targets_walter_tumbling(shin_angle=[[0.5, 0, 0, 0]], shin_angle_prev=[[0.498, 0, 0, 0]],
+                                   shin_angle0=[[0.1, 0, 0, 0]], thigh_z=[[0, 0.30, 0, 0]],
+                                   thigh_z_prev=[[0, 0.301, 0, 0]], thigh_z0=[[0, 0.33, 0, 0]],
+                                   time=0.1, dt=0.002)
+    assert t.shape == (1, 17, 6)
+    # shin tl: 2400 ((0.1 + 4*0.1) - 0.5) + 2400 (4 - 0.002/0.002) = 0 + 2400*3
+    assert abs(t[0, 1, 4] - 7200.0) < 1e-9
+    # thigh tr: 2000 ((0.33 - 0.025) - 0.30) + 300 (0 - (-0.001/0.002)) = 10 + 150
+    assert abs(t[0, 6, 2] - 160.0) < 1e-9
+    nz = np.zeros((17, 6), bool)
+    nz[1:5, 4] = True
+    nz[5:9, 2] = True
+    assert not t[0][~nz].any()   # torso row and contact rows stay zero
