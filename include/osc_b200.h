@@ -141,6 +141,11 @@ int osc_setup(osc_handle *h, void *stream);
  * keeps the warm start), solve_optimization (:589-594) and the torque slice (:631). */
 int osc_step(osc_handle *h, void *stream);
 
+/* osc_step runs two kernels by default: the objective build (CasADi H, f, :529-530) inside the
+ * equilibration kernel, then the solve.  on = 0 selects the three-kernel form (separate
+ * build_qp_kernel) -- same results, kept for measurements of the build kernel alone. */
+int osc_set_fused_build(osc_handle *h, int on);
+
 /* reset_optimization() (:596-601): zero primal/dual warm start. */
 int osc_reset_warm_start(osc_handle *h, void *stream);
 

@@ -38,7 +38,7 @@
 #include <vector>
 
 #ifdef OSC_PHASE_CLOCKS  // developer build only (tools/phase_clocks.py)
-__device__ unsigned long long g_phase_clocks[32];
+__device__ unsigned long long g_phase_clocks[64];
 __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 #if defined(__CUDA_ARCH__)
   if (lane0 == 0) atomicAdd(&g_phase_clocks[k], (unsigned long long)clock64());
@@ -48,6 +48,9 @@ __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 #endif
 }
 #define OSC_TICK(k) osc_tick(k, lane0)
+#define OSC_TICKL(k) osc_tick(k, lane)
+#else
+#define OSC_TICKL(k) ((void)0)
 #endif
 
 #include "osc_params.h"
@@ -89,6 +92,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// shared -> global bulk copy (bulk-group completion), and its two waits: `read` = the source
+// may be overwritten, `all` = the data is in global memory
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
                                          uint64_t* bar) {
   asm volatile(
@@ -123,6 +140,45 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
+}
+
+// The k-loop of the objective build: acc = lower-triangle 8x8 tiles of sum_k (w_k Jx_k)' Jx_k
+// with Jx = [J | r | 0] (r = bias - t rides in padding column nv of the last 8-column block).
+template <class D>
+__device__ __forceinline__ void build_accumulate(
+    const double* __restrict__ Js, const double* __restrict__ rs, const double* __restrict__ w_row,
+    int lane, double (&acc)[((D::NV + 7) / 8) * ((D::NV + 7) / 8 + 1) / 2][2]) {
+  constexpr int NV = D::NV, S = D::S;
+  constexpr int NB8 = (NV + 7) / 8;
+  constexpr int NTILE = NB8 * (NB8 + 1) / 2;
+  constexpr int KSTEPS = (S + 3) / 4;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int q = 0; q < NTILE; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll 2
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const int k = 4 * ks + t;            // this lane's row of J inside the k-step
+    const int kc = k < S ? k : S - 1;    // clamp (weight is 0 beyond S)
+    const double wk = w_row[k];
+    double jb[NB8], ja[NB8];
+#pragma unroll
+    for (int q = 0; q < NB8; ++q) {
+      const int col = 8 * q + g;
+      if (q < NB8 - 1) {
+        jb[q] = Js[kc * NV + col];
+      } else {
+        // last block: columns < nv from J, column nv carries r, the rest is zero
+        const double* src = col < NV ? &Js[kc * NV + col] : &rs[kc];
+        jb[q] = col <= NV ? *src : 0.0;
+      }
+      ja[q] = wk * jb[q];
+    }
+    int tile = 0;
+#pragma unroll
+    for (int mi = 0; mi < NB8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni <= mi; ++ni, ++tile) dmma_m8n8k4(acc[tile][0], acc[tile][1], ja[mi], jb[ni]);
+  }
 }
 
 template <class D>
@@ -188,32 +244,7 @@ build_qp_kernel(const __grid_constant__ Params p, const double* __restrict__ J,
       __syncwarp();
     }
     double acc[NTILE][2];
-#pragma unroll
-    for (int q = 0; q < NTILE; ++q) acc[q][0] = acc[q][1] = 0.0;
-#pragma unroll 2
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-      const int k = 4 * ks + t;            // this lane's row of J inside the k-step
-      const int kc = k < S ? k : S - 1;    // clamp (weight is 0 beyond S)
-      const double wk = w_row[k];
-      double jb[NB8], ja[NB8];
-#pragma unroll
-      for (int q = 0; q < NB8; ++q) {
-        const int col = 8 * q + g;
-        if (q < NB8 - 1) {
-          jb[q] = st.J[kc * NV + col];
-        } else {
-          // last block: columns < nv from J, column nv carries r, the rest is zero
-          const double* src = col < NV ? &st.J[kc * NV + col] : &st.bias[kc];
-          jb[q] = col <= NV ? *src : 0.0;
-        }
-        ja[q] = wk * jb[q];
-      }
-      int tile = 0;
-#pragma unroll
-      for (int mi = 0; mi < NB8; ++mi)
-#pragma unroll
-        for (int ni = 0; ni <= mi; ++ni, ++tile) dmma_m8n8k4(acc[tile][0], acc[tile][1], ja[mi], jb[ni]);
-    }
+    build_accumulate<D>(st.J, st.bias, w_row, lane, acc);
     // C fragment: lane holds C[g][2t], C[g][2t+1] of every tile
     double* H = Hdv + (size_t)env * NV * NV;
     int tile = 0;
@@ -324,8 +355,9 @@ struct SolveArgs {
   int *iters, *status;
   const double* scal;  // scaling records of scale_kernel3
   // work counter: never reset -- a launch over n environments with W warps draws exactly
-  // n + W tickets (every warp draws one past the end), so the host knows where the next
-  // launch's tickets start (`base`) without a memset between the kernels
+  // n + 2 W tickets (every warp draws two past its work: tickets are drawn ahead of their
+  // use), so the host knows where the next launch's tickets start (`base`) without a memset
+  // between the kernels
   unsigned* counter;
   unsigned base;
   // ticket -> environment (a permutation of [0, n_envs), longest expected solves first), or
@@ -342,6 +374,8 @@ struct SolveArgs {
 // environment's bulk copies in flight while the passes run on registers.
 struct ScaleArgs {
   const double *M, *J, *Hdv, *fdv;
+  const double *bias, *targets;  // fused build only
+  double *Hdv_out, *fdv_out;     // fused build only: H, f for the solve kernel
   double* state;  // reads previous f / flag / signature, updates the signature in place
   double* scal;   // out: D, E, c, path flag per environment
   unsigned* counter;  // see SolveArgs
@@ -370,32 +404,178 @@ scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
   static_assert(sizeof(typename RWS::Stage) ==
                     sizeof(double) * (2 * NV * NV + D::NZ * NV + RWS::TAIL + NV),
                 "the landing stage is exactly the five bulk copies");
-  auto fetch = [&]() -> int {
-    int env = 0;
-    if (lane == 0) {
-      env = (int)(atomicAdd(a.counter, 1u) - a.base);
-      if (env < a.n_envs) {
-        fence_proxy_async();
-        mbar_expect_tx(bar, kBytes);
-        bulk_g2s(rw.in.M, a.M + (size_t)env * NV * NV, sizeof(rw.in.M), bar);
-        bulk_g2s(rw.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(rw.in.H), bar);
-        bulk_g2s(rw.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(rw.in.Jc), bar);
-        bulk_g2s(rw.in.tail, a.state + (size_t)env * D::STATE + TAIL0, sizeof(rw.in.tail), bar);
-        bulk_g2s(rw.in.fv, a.fdv + (size_t)env * NV, sizeof(rw.in.fv), bar);
-      }
+  // tickets are drawn one environment ahead of their use (`ticket`: lane 0 only), so that the
+  // round trip of the atomic never stalls the warp; every warp draws two tickets past its work
+  auto draw = [&]() -> int { return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0; };
+  auto fetch = [&](int ticket) -> int {
+    if (lane == 0 && ticket < a.n_envs) {
+      const int env = ticket;
+      fence_proxy_async();
+      mbar_expect_tx(bar, kBytes);
+      bulk_g2s(rw.in.M, a.M + (size_t)env * NV * NV, sizeof(rw.in.M), bar);
+      bulk_g2s(rw.in.H, a.Hdv + (size_t)env * NV * NV, sizeof(rw.in.H), bar);
+      bulk_g2s(rw.in.Jc, a.J + ((size_t)env * D::S + D::JC0) * NV, sizeof(rw.in.Jc), bar);
+      bulk_g2s(rw.in.tail, a.state + (size_t)env * D::STATE + TAIL0, sizeof(rw.in.tail), bar);
+      bulk_g2s(rw.in.fv, a.fdv + (size_t)env * NV, sizeof(rw.in.fv), bar);
     }
-    return __shfl_sync(0xffffffffu, env, 0);
+    return __shfl_sync(0xffffffffu, ticket, 0);
   };
   uint32_t parity = 0;
-  int env = fetch();
+  int env = fetch(draw());
+  int ticket = draw();
   while (env < a.n_envs) {
     mbar_wait(bar, parity);
     parity ^= 1;
     int next = a.n_envs;
     C3::ruiz(rw, p, lane, a.scal + (size_t)env * C3::SCAL,
-             a.state + (size_t)env * D::STATE + D::SIG0, [&]() { next = fetch(); });
+             a.state + (size_t)env * D::STATE + D::SIG0, [&]() {
+               next = fetch(ticket);
+               ticket = draw();
+             });
     env = next;
   }
+}
+
+// K2 + K3a fused: the objective build (DMMA, as in build_qp_kernel) runs in the warp that
+// equilibrates the environment, on the task Jacobian it lands anyway for the contact rows.
+// H and f never make a round trip through HBM before the Ruiz passes (they leave through two
+// bulk stores for the solve kernel), one launch and one kernel tail less per control step,
+// and the HBM-bound read of J hides under the latency-bound passes of the other warps.
+template <class D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+build_scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
+  using RWS = BuildRuizWorkspace<D>;
+  using C3 = Core3<D>;
+  constexpr int NV = D::NV, S = D::S, NS = D::NS, TAIL0 = D::N + 2 * D::M;
+  constexpr int NB8 = (NV + 7) / 8, NTILE = NB8 * (NB8 + 1) / 2, KSTEPS = (S + 3) / 4;
+  static_assert(NV % 8 != 0, "f rides in the zero padding of the last 8-column block");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  RWS* wsb = reinterpret_cast<RWS*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WARPS * sizeof(RWS));
+  double* w_row = reinterpret_cast<double*>(bars + WARPS);  // 4 * KSTEPS, zero padded
+  int* t_idx = reinterpret_cast<int*>(w_row + 4 * KSTEPS);  // index into targets of row k
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RWS& rw = wsb[warp];
+  uint64_t* bar = &bars[warp];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (int k = threadIdx.x; k < 4 * KSTEPS; k += blockDim.x) {
+    w_row[k] = k < S ? p.w_row[k] : 0.0;
+    const int kc = k < S ? k : S - 1;
+    const int kr = (kc < 3 * NS) ? kc : kc - 3 * NS;
+    t_idx[k] = (kr / 3) * 6 + (kr % 3) + ((kc < 3 * NS) ? 0 : 3);  // autogen.py:163,173-177
+  }
+  __syncthreads();
+  constexpr uint32_t kBytes = sizeof(typename RWS::Stage);
+  static_assert(sizeof(typename RWS::Stage) ==
+                    sizeof(double) * (NV * NV + S * NV + 2 * S + RWS::TAIL),
+                "the landing stage is exactly the five bulk copies");
+  // (tickets one environment ahead of their use, see scale_kernel3)
+  auto draw = [&]() -> int { return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0; };
+  auto fetch = [&](int ticket) -> int {
+    if (lane == 0 && ticket < a.n_envs) {
+      const int env = ticket;
+      fence_proxy_async();
+      mbar_expect_tx(bar, kBytes);
+      bulk_g2s(rw.in.M, a.M + (size_t)env * NV * NV, sizeof(rw.in.M), bar);
+      bulk_g2s(rw.in.J, a.J + (size_t)env * S * NV, sizeof(rw.in.J), bar);
+      bulk_g2s(rw.in.bias, a.bias + (size_t)env * S, sizeof(rw.in.bias), bar);
+      bulk_g2s(rw.in.targets, a.targets + (size_t)env * S, sizeof(rw.in.targets), bar);
+      bulk_g2s(rw.in.tail, a.state + (size_t)env * D::STATE + TAIL0, sizeof(rw.in.tail), bar);
+    }
+    return __shfl_sync(0xffffffffu, ticket, 0);
+  };
+  const double two_wreg = 2.0 * p.w_reg;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t parity = 0;
+  int env = fetch(draw());
+  int ticket = draw();
+  while (env < a.n_envs) {
+    OSC_TICKL(40);
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    OSC_TICKL(41);
+    // ---- objective build: r = bias - t in place, then H, f in shared memory
+    {
+      constexpr int RR = (S + 31) / 32;
+      double rv[RR];  // all loads, then all stores (the stores alias the loads for the compiler)
+#pragma unroll
+      for (int j = 0; j < RR; ++j) {
+        const int k = lane + 32 * j;
+        rv[j] = k < S ? rw.in.bias[k] - rw.in.targets[t_idx[k]] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < RR; ++j) {
+        const int k = lane + 32 * j;
+        if (k < S) rw.in.bias[k] = rv[j];
+      }
+    }
+    if (lane == 0) bulk_wait_read();  // the previous environment's H, f have left
+    __syncwarp();
+    {
+      double acc[NTILE][2];
+      OSC_TICKL(42);
+      build_accumulate<D>(rw.in.J, rw.in.bias, w_row, lane, acc);
+      OSC_TICKL(43);
+      int tile = 0;
+#pragma unroll
+      for (int mi = 0; mi < NB8; ++mi) {
+        const int row = 8 * mi + g;
+#pragma unroll
+        for (int ni = 0; ni <= mi; ++ni, ++tile) {
+          const int col = 8 * ni + 2 * t;
+          double v0 = 2.0 * acc[tile][0], v1 = 2.0 * acc[tile][1];
+          if (row < NV && col < NV) {
+            if (mi == ni) {
+              // the lower-triangle value is used for (i,j) and (j,i): exactly symmetric H
+              if (col <= row) {
+                if (col == row) v0 += two_wreg;
+                rw.H[row * NV + col] = v0;
+                if (col != row) rw.H[col * NV + row] = v0;
+              }
+              if (col + 1 <= row) {
+                if (col + 1 == row) v1 += two_wreg;
+                rw.H[row * NV + col + 1] = v1;
+                if (col + 1 != row) rw.H[(col + 1) * NV + row] = v1;
+              }
+            } else {
+              *reinterpret_cast<double2*>(&rw.H[row * NV + col]) = make_double2(v0, v1);
+              rw.H[col * NV + row] = v0;
+              rw.H[(col + 1) * NV + row] = v1;
+            }
+          }
+        }
+      }
+      if (g == NV % 8) {  // f/2 = row (nv mod 8) of the last tile row
+#pragma unroll
+        for (int ni = 0; ni < NB8; ++ni) {
+          const int q = (NB8 - 1) * NB8 / 2 + ni;
+          const int col = 8 * ni + 2 * t;
+          if (col < NV) rw.fv[col] = 2.0 * acc[q][0];
+          if (col + 1 < NV) rw.fv[col + 1] = 2.0 * acc[q][1];
+        }
+      }
+    }
+    fence_proxy_async();  // H, f (generic-proxy stores) before the bulk stores read them
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(a.Hdv_out + (size_t)env * NV * NV, rw.H, sizeof(rw.H));
+      bulk_s2g(a.fdv_out + (size_t)env * NV, rw.fv, sizeof(rw.fv));
+      bulk_commit();
+    }
+    OSC_TICKL(44);
+    int next = a.n_envs;
+    C3::ruiz(rw, p, lane, a.scal + (size_t)env * C3::SCAL,
+             a.state + (size_t)env * D::STATE + D::SIG0, [&]() {
+               next = fetch(ticket);
+               ticket = draw();
+             });
+    OSC_TICKL(45);
+    env = next;
+  }
+  if (lane == 0) bulk_wait_all();
 }
 
 // K3 for robots with 2 nv <= 32: osc::Core3 (register-resident iteration matrices, two lanes
@@ -428,10 +608,12 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   // lane 0 draws the next environment from the work counter (`draw`: issued early, the
   // round trip of the atomic overlaps step_prepare) and later starts landing it (`land`:
   // eight bulk copies into the stage; returns the index to all lanes)
-  auto draw = [&]() -> int {
-    if (lane != 0) return 0;
-    const int t = (int)(atomicAdd(a.counter, 1u) - a.base);
-    return (a.order && t < a.n_envs) ? a.order[t] : t;
+  // Tickets are drawn two environments ahead (`draw`, lane 0), and turned into an environment
+  // index (`resolve`: the hand-out order) one ahead, so that neither the round trip of the
+  // atomic nor the dependent load stalls the warp; every warp draws two tickets past its work.
+  auto draw = [&]() -> int { return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0; };
+  auto resolve = [&](int t) -> int {
+    return (lane == 0 && a.order && t < a.n_envs) ? a.order[t] : t;
   };
   auto land = [&](int env) -> int {
     if (lane == 0 && env < a.n_envs) {
@@ -449,9 +631,18 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     return __shfl_sync(0xffffffffu, env, 0);
   };
   uint32_t parity = 0;
-  int env = land(draw());
+#ifdef OSC_PHASE_CLOCKS  // SM clock rate while this kernel runs: cycles [29] per nanosecond [30]
+  unsigned long long pc_c0 = 0, pc_t0 = 0;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    pc_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc_t0));
+  }
+#endif
+  int env = land(resolve(draw()));
+  int ticket = draw();
   while (env < a.n_envs) {
-    const int drawn = draw();
+    const int drawn = resolve(ticket);
+    ticket = draw();
     mbar_wait(bar, parity);
     parity ^= 1;
     const int lane0 = lane;
@@ -480,6 +671,14 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     OSC_TICK(8);
     env = next;
   }
+#ifdef OSC_PHASE_CLOCKS
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicAdd(&g_phase_clocks[29], (unsigned long long)clock64() - pc_c0);
+    atomicAdd(&g_phase_clocks[30], t1 - pc_t0);
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -878,6 +1077,9 @@ struct osc_handle {
   bool kernels_ready;   // function attributes of the scale / solve kernels are set
   bool build_ready;     // ... of the build kernel (+ its resident grid size)
   bool cond_ready;      // ... of the condensed kernel
+  bool fused_ready;     // ... of the fused build + equilibration kernel
+  bool fuse_build;      // osc_step runs build_scale_kernel3 instead of build + scale (default)
+  bool fuse_now;        // set by osc_step around its launch_solve call
   // optional per-kernel timing
   bool timing;
   std::vector<cudaEvent_t> ev;  // 3 events per recorded step
@@ -984,6 +1186,7 @@ int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   osc::ScaleArgs a;
   a.M = h->iM + e * D::NV * D::NV; a.J = h->iJ + e * D::S * D::NV;
   a.Hdv = h->dH + e * D::NV * D::NV; a.fdv = h->dF + e * D::NV;
+  a.bias = a.targets = nullptr; a.Hdv_out = a.fdv_out = nullptr;
   a.state = h->dState + e * D::STATE;
   a.scal = h->dScal + e * osc::Core3<D>::SCAL;
   a.counter = reinterpret_cast<unsigned*>(h->dCounter) + slot;
@@ -991,7 +1194,43 @@ int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
-  h->ctr_base[slot] += (unsigned)n + (unsigned)(grid * WARPS);
+  h->ctr_base[slot] += (unsigned)n + 2u * (unsigned)(grid * WARPS);
+  h->launches++;
+  return OSC_OK;
+}
+
+// fused objective build + equilibration (build_scale_kernel3): same warps per CTA as the
+// equilibration alone; the landing stage grows by the task Jacobian
+template <class D>
+int launch_build_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
+  constexpr int WARPS = scale3_warps<D>();
+  constexpr int KSTEPS = (D::S + 3) / 4;
+  constexpr size_t smem = WARPS * sizeof(osc::BuildRuizWorkspace<D>) + WARPS * sizeof(uint64_t) +
+                          4 * KSTEPS * (sizeof(double) + sizeof(int));
+  static_assert(smem <= 227 * 1024, "shared memory per CTA");
+  auto kern = osc::build_scale_kernel3<D, WARPS>;
+  if (!h->fused_ready) {
+    OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->fused_ready = true;
+  }
+  int grid = h->sm_count;
+  const int need = (n + WARPS - 1) / WARPS;
+  if (grid > need) grid = need;
+  const int slot = h->n_counters + 1 + counter;  // second bank of work counters
+  const size_t e = (size_t)env0;
+  osc::ScaleArgs a;
+  a.M = h->iM + e * D::NV * D::NV; a.J = h->iJ + e * D::S * D::NV;
+  a.Hdv = nullptr; a.fdv = nullptr;
+  a.bias = h->iBias + e * D::S; a.targets = h->iTargets + e * D::S;
+  a.Hdv_out = h->dH + e * D::NV * D::NV; a.fdv_out = h->dF + e * D::NV;
+  a.state = h->dState + e * D::STATE;
+  a.scal = h->dScal + e * osc::Core3<D>::SCAL;
+  a.counter = reinterpret_cast<unsigned*>(h->dCounter) + slot;
+  a.base = h->ctr_base[slot];
+  a.n_envs = n;
+  kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
+  OSC_CUDA(h, cudaGetLastError());
+  h->ctr_base[slot] += (unsigned)n + 2u * (unsigned)(grid * WARPS);
   h->launches++;
   return OSC_OK;
 }
@@ -1021,14 +1260,15 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
-  h->ctr_base[counter] += (unsigned)n + (unsigned)(grid * WARPS);
+  h->ctr_base[counter] += (unsigned)n + 2u * (unsigned)(grid * WARPS);
   h->launches++;
   return OSC_OK;
 }
 
 template <class D>
 int launch_solve3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) {
-  int rc = launch_scale3<D>(h, st, env0, n, counter);
+  int rc = h->fuse_now ? launch_build_scale3<D>(h, st, env0, n, counter)
+                       : launch_scale3<D>(h, st, env0, n, counter);
   if (rc) return rc;
   if (h->timing_mid) OSC_CUDA(h, cudaEventRecord(h->timing_mid, st));
   return launch_solve3w<D, solve3_warps<D>()>(h, st, env0, n, counter);
@@ -1246,6 +1486,9 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   h->kernels_ready = false;
   h->build_ready = false;
   h->cond_ready = false;
+  h->fused_ready = false;
+  h->fuse_build = true;
+  h->fuse_now = false;
   h->build_grid_max = h->sm_count;
   *out = h;
   return OSC_OK;
@@ -1346,19 +1589,30 @@ int osc_step(osc_handle* h, void* stream) {
     h->ev_used += 4;
     OSC_CUDA(h, cudaEventRecord(ev[0], st));
   }
-  int rc = OSC_DISPATCH(h, launch_build, h, st, 0, h->n_envs);
+  int rc = OSC_OK;
+  // the objective build runs inside the equilibration kernel (build_scale_kernel3) unless the
+  // caller asked for the three-kernel form (osc_set_fused_build: measurements, A/B tests)
+  if (!h->fuse_build) rc = OSC_DISPATCH(h, launch_build, h, st, 0, h->n_envs);
   if (rc) return rc;
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[1], st));
   // ev[2] = scale | solve boundary: recorded by launch_solve3 between its two kernels
   h->timing_mid = ev ? ev[2] : nullptr;
   h->use_order = ordered;
+  h->fuse_now = h->fuse_build;
   rc = OSC_DISPATCH(h, launch_solve, h, st, 0, h->n_envs, 0);
+  h->fuse_now = false;
   h->use_order = false;
   h->timing_mid = nullptr;
   if (rc) return rc;
   if (ordered) h->order_age++;
   h->kernels_ready = true;  // function attributes / occupancy are set from here on
   if (ev) OSC_CUDA(h, cudaEventRecord(ev[3], st));
+  return OSC_OK;
+}
+
+int osc_set_fused_build(osc_handle* h, int on) {
+  if (check_handle(h)) return OSC_ERR_INVALID;
+  h->fuse_build = on != 0;
   return OSC_OK;
 }
 
@@ -1558,9 +1812,11 @@ static int step_host_few(osc_handle* h, const double* M, const double* C, const 
   std::memcpy(h->hIn + h->in_off[4], targets, N * s * B);
   std::memcpy(h->hIn + h->in_off[5], mask, N * nc * B);
   OSC_CUDA(h, cudaMemcpyAsync(h->dIn, h->hIn, h->in_doubles * B, cudaMemcpyHostToDevice, st));
-  int rc = OSC_DISPATCH(h, launch_build, h, st, 0, (int)N);
+  int rc = h->fuse_build ? OSC_OK : OSC_DISPATCH(h, launch_build, h, st, 0, (int)N);
   if (rc) return rc;
+  h->fuse_now = h->fuse_build;
   rc = OSC_DISPATCH(h, launch_solve, h, st, 0, (int)N, 0);
+  h->fuse_now = false;
   if (rc) return rc;
   OSC_CUDA(h, cudaMemcpyAsync(h->hTq, h->dTorque, N * nu * B, cudaMemcpyDeviceToHost, st));
   h->kernels_ready = true;
@@ -1632,9 +1888,11 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
     OSC_CUDA(h, cudaMemcpyAsync(h->dMask + e0 * nc, mask + e0 * nc, n * nc * B, cudaMemcpyHostToDevice, cs));
     OSC_CUDA(h, cudaEventRecord(h->chunk_ev[c], cs));
     OSC_CUDA(h, cudaStreamWaitEvent(st, h->chunk_ev[c], 0));
-    int rc = OSC_DISPATCH(h, launch_build, h, st, (int)e0, (int)n);
+    int rc = h->fuse_build ? OSC_OK : OSC_DISPATCH(h, launch_build, h, st, (int)e0, (int)n);
     if (rc) return rc;
+    h->fuse_now = h->fuse_build;
     rc = OSC_DISPATCH(h, launch_solve, h, st, (int)e0, (int)n, c);
+    h->fuse_now = false;
     if (rc) return rc;
     OSC_CUDA(h, cudaMemcpyAsync(torque + e0 * nu, h->dTorque + e0 * nu, n * nu * B, cudaMemcpyDeviceToHost, st));
   }
@@ -1651,10 +1909,10 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
 
 #ifdef OSC_PHASE_CLOCKS
 int osc_debug_phase_clocks(unsigned long long* out16, int reset) {
-  if (cudaMemcpyFromSymbol(out16, ::g_phase_clocks, 32 * sizeof(unsigned long long)) != cudaSuccess)
+  if (cudaMemcpyFromSymbol(out16, ::g_phase_clocks, 64 * sizeof(unsigned long long)) != cudaSuccess)
     return OSC_ERR_CUDA;
   if (reset) {
-    unsigned long long z[32] = {0};
+    unsigned long long z[64] = {0};
     if (cudaMemcpyToSymbol(::g_phase_clocks, z, sizeof(z)) != cudaSuccess) return OSC_ERR_CUDA;
   }
   return OSC_OK;

@@ -33,6 +33,15 @@
 
 namespace osc {
 
+// a value the compiler must keep in a register instead of recomputing it from the lane index
+// wherever it is used (index arithmetic inside the iteration loop)
+OSC_HD int osc_opaque(int v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+
 #if defined(__CUDA_ARCH__)
 
 template <class T>

@@ -32,6 +32,7 @@ EXPORTS = (
     "osc_gather_create", "osc_gather_attach", "osc_gather_torques", "osc_gather_buffers",
     "osc_step_condensed", "osc_reset_condensed", "osc_kinematics",
     "osc_walter_tumbling_default_gains", "osc_targets_walter_tumbling",
+    "osc_set_fused_build",
 )
 KIN_MAX_BODIES = 16
 IPC_HANDLE_BYTES = 64
@@ -443,6 +444,11 @@ class BatchedOSC:
         a, b = C.c_size_t(0), C.c_size_t(0)
         self._check(self.L.osc_host_traffic(self.h, C.byref(a), C.byref(b)), "osc_host_traffic")
         return a.value, b.value
+
+    def set_fused_build(self, on: bool = True):
+        """osc_step as two kernels (objective build inside the equilibration kernel; default)
+        or three (separate build_qp_kernel).  Same results."""
+        self._check(self.L.osc_set_fused_build(self.h, int(on)), "osc_set_fused_build")
 
     def enable_timing(self, on: bool = True):
         self._check(self.L.osc_timing_enable(self.h, int(on)), "osc_timing_enable")

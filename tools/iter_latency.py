@@ -8,10 +8,13 @@ import numpy as np
 import osc_b200 as ob
 from osc_b200 import capi
 
+if os.environ.get("OSC_LIB"):  # a developer build of the library (tools/_build/)
+    capi.LIB_PATH = os.environ["OSC_LIB"]
 preset = sys.argv[1] if len(sys.argv) > 1 else "walter_sr_true_tumbling_mjjoint"
 config = sys.argv[2] if len(sys.argv) > 2 else "tumbling"
 spec = ob.load_preset(preset)
-for n_envs in (1, 4, 8, 148, 1184, 16384):
+sizes = [int(a) for a in sys.argv[3:]] or [1, 4, 8, 148, 1184, 16384]
+for n_envs in sizes:
     res = {}
     for K in (200, 1200):
         st = capi.default_settings(eps_abs=0.0, eps_rel=0.0, max_iter=K, check_termination=0,

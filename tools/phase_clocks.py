@@ -40,7 +40,7 @@ def main():
     steps = [ob.synth.make_inputs(spec, N, config, step=t) for t in range(3)]
     g = capi.BatchedOSC(spec, N)
     g.enable_timing(True)
-    buf = (C.c_ulonglong * 32)()
+    buf = (C.c_ulonglong * 64)()
 
     def report(tag):
         L.osc_debug_phase_clocks(buf, 1)
@@ -54,12 +54,25 @@ def main():
                 ("set_rho + factor", d(3, 2)), ("  Kd build", d(9, 2)), ("  Kd_dv^-1 (sweep)", d(10, 9)),
                 ("  W products", d(11, 10)), ("  S product", d(12, 11)), ("  S^-1 + register loads", d(3, 12)),
                 ("iterations", d(5, 4)), ("residuals", d(6, 5)), ("termination / rho update", d(7, 6)),
-                ("outputs", d(8, 16)), ("whole solve part", d(8, 2)), ("environment total (excl. wait)", d(8, 0))]
+                ("outputs", d(8, 16)), ("  1 / c", d(32, 16)), ("  solution, state stores", d(33, 32)),
+                ("  result scalars", d(8, 33)),
+                ("residuals: exchange + group shuffles", d(34, 5)), ("residuals: rows, columns", d(35, 34)),
+                ("residuals: maxima", d(36, 35)), ("residuals: reduce", d(6, 36)),
+                ("whole solve part", d(8, 2)), ("environment total (excl. wait)", d(8, 0))]
         print(f"--- {tag}: solve kernel {kt.solve_ms:.3f} ms, iters mean {r['iters'].mean():.1f}")
         for k, v in rows:
             print(f"  {k:34s} {v:10.0f} cycles/env")
         it = r["iters"].mean()
         print(f"  cycles per iteration               {d(5, 4) / it:10.0f}")
+        if t[45] != 0:
+            print("  fused build + equilibration kernel (cycles/env at its own occupancy):")
+            for k, v in [("wait for the landing stage", d(41, 40)), ("r = bias - t", d(42, 41)),
+                         ("J'WJ (DMMA)", d(43, 42)), ("H, f -> shared + bulk stores", d(44, 43)),
+                         ("Ruiz passes", d(45, 44)), ("total", d(45, 40))]:
+                print(f"    {k:32s} {v:10.0f}")
+        if t[30] > 0:
+            print(f"  SM clock while the kernel ran (clock64 / globaltimer of CTA 0): {1e3 * t[29] / t[30]:.0f} MHz "
+                  f"over {t[30] / 1e3:.1f} us")
 
     if "--condensed" in sys.argv:
         def creport(tag):

@@ -11,6 +11,8 @@ def main():
     preset = sys.argv[1] if len(sys.argv) > 1 else "walter_sr_true_tumbling_mjjoint"
     config = sys.argv[2] if len(sys.argv) > 2 else "tumbling"
     N = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
+    if os.environ.get("OSC_LIB"):  # a developer build of the library (tools/_build/)
+        capi.LIB_PATH = os.environ["OSC_LIB"]
     spec = ob.load_preset(preset)
     print("dfma peak TF/s", capi.measure_dfma_tflops(0))
     t0 = time.time()
