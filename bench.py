@@ -15,8 +15,10 @@ e2e        same metric through the C-ABI with pinned HOST buffers: H2D of the st
            inputs + step + D2H of the torques inside the timed region
 roofline   dominant kernel (solve_kernel3 for the Walter robots: assembly, factorisation,
            ADMM): algorithmic FLOPs / CUDA-event time vs the measured FP64-FMA peak;
-           `roofline_scale` is the equilibration kernel (FP64 pipe: mul + compare per entry
-           and pass), `roofline_build` the HBM-bound objective-build kernel
+           `roofline_scale` is the fused objective-build + equilibration kernel
+           (build_scale_kernel3; FP64 pipe: one MAC per entry of J'WJ, one mul + compare per
+           matrix entry and Ruiz pass); `roofline_build` the HBM-bound stand-alone build kernel
+           (build_qp_kernel), timed in the three-kernel form of the step (`three_kernel_form`)
 cpu_baseline  the oracle (restatement of the reference's CPU path, "port") on the box's
            host cores, bounded sample, same protocol
 --impl reference   times that CPU path alone (rank 0 only).
@@ -105,6 +107,11 @@ def scale_ops_per_solve(spec, passes=10):
     nnz_p = nv * nv + (n - nv)
     nnz_a = nv * (nv + 3 * nc) + nu + 12 * nc + n
     return passes * 2 * (nnz_p + 2 * nnz_a)
+
+
+def build_macs_per_solve(spec):
+    """Objective build: lower triangle of J'WJ (rows with a weight) and f = 2 J'W(bias - t)."""
+    return spec.s * (spec.nv * (spec.nv + 1) // 2 + spec.nv)
 
 
 def build_bytes_per_solve(spec):
@@ -267,16 +274,13 @@ def measure_resident(ob, capi, sharding, torch, spec, wl, n_envs, steps, warmup,
            "p50_batch_latency_ms": p50, "iters_mean": float(res["iters"].mean()),
            "solved_frac": float((res["status"] == capi.SOLVED).mean()),
            "inputs_exceed_l2": bool(nsets * in_bytes > 126e6),
-           "kernel_ms": {"build_qp_kernel": kt.build_ms, "scale_kernel3": kt.scale_ms,
-                         "solve_kernel3": kt.solve_ms},
+           "kernel_ms": {"build_scale_kernel3": kt.scale_ms, "solve_kernel3": kt.solve_ms},
            "roofline": {"kernel": "solve_kernel3", "bound": "fp64_fma",
                         "achieved": flops / (kt.solve_ms * 1e-3) / 1e12, "peak": dfma,
                         "unit": "TFLOP/s",
                         "frac": flops / (kt.solve_ms * 1e-3) / 1e12 / dfma},
-           "roofline_scale_frac": scale_ops_per_solve(spec, 10) * n_envs
-                                  / (kt.scale_ms * 1e-3) / 1e12 / (dfma / 2.0),
-           "roofline_build_frac": build_bytes_per_solve(spec) * n_envs
-                                  / (kt.build_ms * 1e-3) / 1e9 / hbm_peak}
+           "roofline_scale_frac": (scale_ops_per_solve(spec, 10) + build_macs_per_solve(spec))
+                                  * n_envs / (kt.scale_ms * 1e-3) / 1e12 / (dfma / 2.0)}
     if with_dual:
         # contacts whose friction pyramid is active at the solution: a friction row with a
         # positive multiplier (rows nv .. nv + 4 nc of the dual) on an unmasked contact
@@ -573,6 +577,28 @@ def main():
     cold_ms = sharding.max_over_ranks(c0.elapsed_time(c1), dev)
     cold_iters = float(osc.results(stream)["iters"].mean())
 
+    # ---- the three-kernel form of the step (stand-alone build_qp_kernel + scale_kernel3 +
+    #      solve_kernel3; same results): what the fusion of the objective build into the
+    #      equilibration kernel buys, and the HBM roofline of the build kernel on its own
+    osc.set_fused_build(False)
+    for t in range(args.warmup):
+        bind(t)
+        osc.step_device(stream)
+    osc.enable_timing(True)
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n3 = max(10, min(args.steps, 50))
+    u0.record()
+    for t in range(args.warmup, args.warmup + n3):
+        bind(t)
+        osc.step_device(stream)
+    u1.record()
+    barrier()
+    ms3 = sharding.max_over_ranks(u0.elapsed_time(u1), dev) / n3
+    kt3 = osc.read_timing()
+    osc.enable_timing(False)
+    osc.set_fused_build(True)
+
     # ---- end to end through the C-ABI with host buffers (e2e)
     osc.bind_device_inputs()  # back to the handle's own input buffers
     tq = capi.pinned_empty((n_envs, spec.nu))
@@ -716,7 +742,7 @@ def main():
     dfma_peak = capi.measure_dfma_tflops(local)
     flops = algorithmic_flops_per_solve(spec, res["iters"]) * n_envs
     solve_tflops = flops / (kt.solve_ms * 1e-3) / 1e12
-    build_gbs = build_bytes_per_solve(spec) * n_envs / (kt.build_ms * 1e-3) / 1e9
+    build_gbs = build_bytes_per_solve(spec) * n_envs / (kt3.build_ms * 1e-3) / 1e9
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -731,28 +757,40 @@ def main():
                 "peak_source": "DFMA micro-benchmark run inside this bench "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_solve": flops / n_envs, "iters_mean": k_mean,
-                "ncu": "latency-bound: 8 warps/SM at 255 registers, issue slots 37 %, FP64 "
-                       "pipe 33 %, shared-memory pipe 67 % of peak (profiles/r1q_ncu_summary.md)",
+                "ncu": "latency-bound: 8 warps/SM at 255 registers (registers are granted per four "
+                       "warps: the next step is 12 warps at 168), issue slots 39 %, FP64 pipe 34 %, "
+                       "shared-memory pipe 57 % of peak (profiles/r3_ncu_summary.md)",
                 "launch_ms": kt.solve_ms,
                 "hbm_view": {"achieved_gbs": spec.algorithmic_bytes * n_envs
                              / ((kt.solve_ms + kt.scale_ms) * 1e-3) / 1e9,
                              "peak_gbs": hbm_peak}}
     roofline_scale = None
     if split:
-        ops = scale_ops_per_solve(spec, 10) * n_envs
+        ops = (scale_ops_per_solve(spec, 10) + build_macs_per_solve(spec)) * n_envs
         t_ops = ops / (kt.scale_ms * 1e-3) / 1e12
-        roofline_scale = {"kernel": "scale_kernel3", "bound": "fp64_pipe", "achieved": t_ops,
-                          "peak": dfma_peak / 2.0, "unit": "Tops/s (FP64 mul / compare)",
+        roofline_scale = {"kernel": "build_scale_kernel3", "bound": "fp64_pipe", "achieved": t_ops,
+                          "peak": dfma_peak / 2.0,
+                          "unit": "Tops/s (FP64 MAC of J'WJ / mul / compare)",
                           "frac": t_ops / (dfma_peak / 2.0),
-                          "traffic": tr.get("scale_kernel3_dram_bytes_per_launch"),
+                          "traffic": tr.get("build_scale_kernel3_dram_bytes_per_launch"),
                           "peak_source": "half the DFMA FLOP rate: one FP64-pipe instruction "
-                                         "per lane per op",
-                          "algorithmic_ops_per_solve": ops / n_envs, "launch_ms": kt.scale_ms}
+                                         "per lane per op (a DMMA m8n8k4 occupies the pipe like "
+                                         "the 8 DFMAs per lane it replaces)",
+                          "algorithmic_ops_per_solve": ops / n_envs,
+                          "of_which_objective_build": build_macs_per_solve(spec),
+                          "launch_ms": kt.scale_ms}
     roofline_build = {"kernel": "build_qp_kernel", "bound": "hbm", "achieved": build_gbs,
                       "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
                       "traffic": tr.get("build_qp_kernel_dram_bytes_per_launch"),
-                      "peak_source": hbm_src, "launch_ms": kt.build_ms,
-                      "algorithmic_bytes_per_solve": build_bytes_per_solve(spec)}
+                      "peak_source": hbm_src, "launch_ms": kt3.build_ms,
+                      "algorithmic_bytes_per_solve": build_bytes_per_solve(spec),
+                      "note": "stand-alone build kernel, timed in the three-kernel form of the "
+                              "step (osc_set_fused_build(0)); the default step runs the build "
+                              "inside build_scale_kernel3"}
+    three_kernel_form = {"ms_per_step": ms3, "value": world * n_envs / (ms3 * 1e-3), "steps": n3,
+                         "kernel_ms": {"build_qp_kernel": kt3.build_ms,
+                                       "scale_kernel3": kt3.scale_ms,
+                                       "solve_kernel3": kt3.solve_ms}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -773,9 +811,8 @@ def main():
                              "PCIe switch / socket share its bandwidth (see per-rank rates)"},
             "gpu_launches": int(stats["launches"]),
             "roofline": roofline, "roofline_scale": roofline_scale,
-            "roofline_build": roofline_build,
-            "kernel_ms": {"build_qp_kernel": kt.build_ms, "scale_kernel3": kt.scale_ms,
-                          solve_name: kt.solve_ms},
+            "roofline_build": roofline_build, "three_kernel_form": three_kernel_form,
+            "kernel_ms": {"build_scale_kernel3": kt.scale_ms, solve_name: kt.solve_ms},
             "p50_batch_latency_ms": p50_ms,
             "solved_frac": stats["solved"] / (world * n_envs),
             "cold_start": {"ms_per_step": cold_ms, "value": world * n_envs / (cold_ms * 1e-3),

@@ -53,6 +53,13 @@ __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 #define OSC_TICKL(k) ((void)0)
 #endif
 
+// solve kernel: work tickets a warp holds beyond the environment it has landed (1: drawn before
+// the assembly, turned into an environment index after it; 2: one more environment ahead --
+// measured worse on batches of a few waves, where reserved tickets cannot be stolen)
+#ifndef OSC_TICKET_AHEAD
+#define OSC_TICKET_AHEAD 1
+#endif
+
 #include "osc_params.h"
 #include "osc_condensed.cuh"
 #include "osc_kinematics.cuh"
@@ -583,8 +590,12 @@ build_scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
 // warp owns a landing stage for one environment's input record; as soon as step_prepare() has
 // consumed it the warp draws its next environment and lands it there with TMA bulk copies
 // while step_solve() factorises and iterates on the current one.
+constexpr int max_regs_for(int warps) {  // registers per thread that let `warps` warps share an SM
+  const int r = (65536 / (warps * 32)) / 8 * 8;
+  return r > 255 ? 255 : r;
+}
 template <class D, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(max_regs_for(WARPS))
 solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   using WS = Workspace3<D>;
   using C3 = Core3<D>;
@@ -639,10 +650,17 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   }
 #endif
   int env = land(resolve(draw()));
+#if OSC_TICKET_AHEAD == 2
   int ticket = draw();
+#endif
   while (env < a.n_envs) {
-    const int drawn = resolve(ticket);
+#if OSC_TICKET_AHEAD == 2
+    int drawn = resolve(ticket);
     ticket = draw();
+#else
+    const int ticket = draw();
+    int drawn = 0;
+#endif
     mbar_wait(bar, parity);
     parity ^= 1;
     const int lane0 = lane;
@@ -652,7 +670,12 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     double* sx = a.sol_x + (size_t)env * D::N;
     double* sy = a.sol_y + (size_t)env * D::M;
     double* so = a.state + (size_t)env * D::STATE;
+#if OSC_TICKET_AHEAD == 2
     const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy, so);
+#else
+    const typename C3::Prepared pr =
+        C3::step_prepare(w, p, L, lane, sx, sy, so, [&]() { drawn = resolve(ticket); });
+#endif
     __syncwarp();
     OSC_TICK(1);
     const int next = land(drawn);
@@ -1078,6 +1101,7 @@ struct osc_handle {
   bool build_ready;     // ... of the build kernel (+ its resident grid size)
   bool cond_ready;      // ... of the condensed kernel
   bool fused_ready;     // ... of the fused build + equilibration kernel
+  bool scale_ready;     // ... of the stand-alone equilibration kernel
   bool fuse_build;      // osc_step runs build_scale_kernel3 instead of build + scale (default)
   bool fuse_now;        // set by osc_step around its launch_solve call
   // optional per-kernel timing
@@ -1160,10 +1184,15 @@ int launch_reset(osc_handle* h, cudaStream_t st) {
 
 // solve_kernel3: at most 8 warps per CTA (255 registers per thread), fewer when 8 workspaces
 // (landing stage included) do not fit in 227 KB of shared memory
+// (Registers are allocated to a CTA in units of four warps: 9 or 10 warps at 224 / 200
+// registers do not launch.  The next step after 8 warps at 255 registers is 12 at 168.)
+#ifndef OSC_SOLVE_WARPS
+#define OSC_SOLVE_WARPS 8
+#endif
 template <class D>
 constexpr int solve3_warps() {
   constexpr int fit = (int)((227 * 1024 - 128) / sizeof(osc::Workspace3<D>));
-  return fit > 8 ? 8 : fit;
+  return fit > OSC_SOLVE_WARPS ? OSC_SOLVE_WARPS : fit;
 }
 // scale_kernel3: 12 warps per CTA at 168 registers when two lanes share a row (16 warps at 128
 // registers spill a little and measured the same 0.17 ms); rows held by one lane need more
@@ -1176,8 +1205,10 @@ int launch_scale3(osc_handle* h, cudaStream_t st, int env0, int n, int counter) 
   constexpr int WARPS = scale3_warps<D>();
   const size_t smem = WARPS * sizeof(osc::RuizWorkspace<D>) + WARPS * sizeof(uint64_t);
   auto kern = osc::scale_kernel3<D, WARPS>;
-  if (!h->kernels_ready)
+  if (!h->scale_ready) {
     OSC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->scale_ready = true;
+  }
   int grid = h->sm_count;
   const int need = (n + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
@@ -1260,7 +1291,7 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
-  h->ctr_base[counter] += (unsigned)n + 2u * (unsigned)(grid * WARPS);
+  h->ctr_base[counter] += (unsigned)n + (unsigned)OSC_TICKET_AHEAD * (unsigned)(grid * WARPS);
   h->launches++;
   return OSC_OK;
 }
@@ -1487,6 +1518,7 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   h->build_ready = false;
   h->cond_ready = false;
   h->fused_ready = false;
+  h->scale_ready = false;
   h->fuse_build = true;
   h->fuse_now = false;
   h->build_grid_max = h->sm_count;

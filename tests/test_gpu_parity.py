@@ -1027,3 +1027,43 @@ def test_walter_tumbling_target_laws_on_device():
     with pytest.raises(capi.OscError):
         go2.targets_walter_tumbling(*[dev[k].data_ptr() for k in ("sa", "sp", "s0", "tz", "tp", "t0")],
                                     time=0.0, dt=0.002)
+
+
+@pytest.mark.parametrize("preset,config,n_envs", [("walter_sr_true_tumbling_mjjoint", "tumbling", 1501),
+                                                  ("unitree_go2", "go2_standing", 777)])
+def test_fused_build_gives_the_three_kernel_results_bit_for_bit(preset, config, n_envs):
+    """osc_step runs the objective build inside the equilibration kernel
+    (build_scale_kernel3) by default; osc_set_fused_build(0) selects build_qp_kernel +
+    scale_kernel3.  Both accumulate H and f in the same order, so every output of a cold and
+    two warm steps -- and the H, f the step leaves behind -- must be identical, not just close
+    (ragged batch sizes: the last CTA is partly empty)."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    steps = [ob.synth.make_inputs(spec, n_envs, config, step=t) for t in range(3)]
+    out = []
+    for fused in (True, False):
+        g = capi.BatchedOSC(spec, n_envs)
+        g.set_fused_build(fused)
+        g.setup(steps[0])
+        launches0 = g.kernel_launches
+        per = []
+        for inp in steps:
+            g.upload(inp)
+            g.step_device()
+            r = g.results()
+            H, f = g.objective()
+            per.append((r, H, f))
+        out.append((per, g.kernel_launches - launches0))
+        g.set_fused_build(not fused)  # switching on a live handle works, too
+        g.upload(steps[0])
+        g.step_device()
+        assert (g.results()["status"] == capi.SOLVED).mean() > 0.99
+        g.close()
+    (a, la), (b, lb) = out
+    assert lb - la == len(steps), (la, lb)  # one launch less per step
+    for (ra, Ha, fa), (rb, Hb, fb) in zip(a, b):
+        assert np.array_equal(Ha, Hb) and np.array_equal(fa, fb)
+        for k in ("iters", "status", "torque", "x", "y", "rho", "pri_res", "dua_res"):
+            assert np.array_equal(ra[k], rb[k], equal_nan=True) if ra[k].dtype.kind == "f" \
+                else np.array_equal(ra[k], rb[k]), k

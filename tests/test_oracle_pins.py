@@ -340,3 +340,26 @@ def test_sparsity_change_takes_reinit_path(oracle):
     b.step(s0)
     o = b.step(s1)
     assert o["reinits"] == N and (o["status"] == oracle.STATUS_SOLVED).all()
+
+
+@pytest.mark.parametrize("preset,config", [("walter_sr_true_tumbling_mjjoint", "tumbling"),
+                                           ("unitree_go2", "go2_standing")])
+def test_duals_of_the_unbounded_identity_rows_are_exactly_zero(oracle, preset, config):
+    """The identity rows of the dv variables have bounds -/+ OSQP_INFTY (rho = RHO_MIN, no
+    projection): z_new = z_relaxed + y / rho, y += rho (z_relaxed - z_new) keeps y == 0
+    exactly from a cold start on, in every linear-solver form, over cold and warm steps and in
+    the scaled iterates.  The two-lane iteration of the device (osc_core3.cuh iterate_pair)
+    relies on it: it carries neither y nor rho of these rows."""
+    import osc_b200 as ob
+    spec = ob.load_preset(preset)
+    n_envs = 64
+    rb = spec.nv + 4 * spec.nc  # first identity row
+    for linsys in (0, 1):
+        b = oracle.OracleBatch(spec, n_envs, oracle.default_settings(linsys=linsys))
+        b.setup(ob.synth.make_inputs(spec, n_envs, config, step=0))
+        for t in range(3):
+            o = b.step(ob.synth.make_inputs(spec, n_envs, config, step=t))
+            ok = o["status"] == 1
+            assert ok.any()
+            assert not np.any(o["y"][ok, rb:rb + spec.nv]), (linsys, t)
+            assert not np.any(b.scaled_state(0)["y"][rb:rb + spec.nv])
