@@ -53,13 +53,6 @@ __host__ __device__ __forceinline__ void osc_tick(int k, int lane0) {
 #define OSC_TICKL(k) ((void)0)
 #endif
 
-// solve kernel: work tickets a warp holds beyond the environment it has landed (1: drawn before
-// the assembly, turned into an environment index after it; 2: one more environment ahead --
-// measured worse on batches of a few waves, where reserved tickets cannot be stolen)
-#ifndef OSC_TICKET_AHEAD
-#define OSC_TICKET_AHEAD 1
-#endif
-
 #include "osc_params.h"
 #include "osc_condensed.cuh"
 #include "osc_kinematics.cuh"
@@ -413,8 +406,13 @@ scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
                 "the landing stage is exactly the five bulk copies");
   // tickets are drawn one environment ahead of their use (`ticket`: lane 0 only), so that the
   // round trip of the atomic never stalls the warp; every warp draws two tickets past its work
-  auto draw = [&]() -> int { return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0; };
-  auto fetch = [&](int ticket) -> int {
+  auto draw = [&]() -> unsigned {  // only the atomic: its result is first touched in fetch()
+    unsigned raw = 0;
+    if (lane == 0) raw = atomicAdd(a.counter, 1u);
+    return raw;
+  };
+  auto fetch = [&](unsigned raw) -> int {
+    const int ticket = (int)(raw - a.base);
     if (lane == 0 && ticket < a.n_envs) {
       const int env = ticket;
       fence_proxy_async();
@@ -429,7 +427,7 @@ scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
   };
   uint32_t parity = 0;
   int env = fetch(draw());
-  int ticket = draw();
+  unsigned ticket = draw();
   while (env < a.n_envs) {
     mbar_wait(bar, parity);
     parity ^= 1;
@@ -480,8 +478,13 @@ build_scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
                     sizeof(double) * (NV * NV + S * NV + 2 * S + RWS::TAIL),
                 "the landing stage is exactly the five bulk copies");
   // (tickets one environment ahead of their use, see scale_kernel3)
-  auto draw = [&]() -> int { return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0; };
-  auto fetch = [&](int ticket) -> int {
+  auto draw = [&]() -> unsigned {  // only the atomic: its result is first touched in fetch()
+    unsigned raw = 0;
+    if (lane == 0) raw = atomicAdd(a.counter, 1u);
+    return raw;
+  };
+  auto fetch = [&](unsigned raw) -> int {
+    const int ticket = (int)(raw - a.base);
     if (lane == 0 && ticket < a.n_envs) {
       const int env = ticket;
       fence_proxy_async();
@@ -498,7 +501,7 @@ build_scale_kernel3(const __grid_constant__ Params p, const ScaleArgs a) {
   const int g = lane >> 2, t = lane & 3;
   uint32_t parity = 0;
   int env = fetch(draw());
-  int ticket = draw();
+  unsigned ticket = draw();
   while (env < a.n_envs) {
     OSC_TICKL(40);
     mbar_wait(bar, parity);
@@ -619,11 +622,19 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   // lane 0 draws the next environment from the work counter (`draw`: issued early, the
   // round trip of the atomic overlaps step_prepare) and later starts landing it (`land`:
   // eight bulk copies into the stage; returns the index to all lanes)
-  // Tickets are drawn two environments ahead (`draw`, lane 0), and turned into an environment
-  // index (`resolve`: the hand-out order) one ahead, so that neither the round trip of the
-  // atomic nor the dependent load stalls the warp; every warp draws two tickets past its work.
-  auto draw = [&]() -> int { return lane == 0 ? (int)(atomicAdd(a.counter, 1u) - a.base) : 0; };
-  auto resolve = [&](int t) -> int {
+  // Work tickets (lane 0).  `draw` only issues the atomic: nothing touches its result until
+  // `resolve` turns it into an environment index (ticket - base, then the hand-out order), so
+  // the round trip never stalls the warp.  A ticket is drawn just before the output stores of
+  // one environment, resolved at the top of the next (the dependent load of the order then
+  // has the whole assembly to arrive) and landed after that environment's assembly.  Every
+  // warp draws two tickets past its work.
+  auto draw = [&]() -> unsigned {
+    unsigned raw = 0;
+    if (lane == 0) raw = atomicAdd(a.counter, 1u);
+    return raw;
+  };
+  auto resolve = [&](unsigned raw) -> int {
+    const int t = (int)(raw - a.base);
     return (lane == 0 && a.order && t < a.n_envs) ? a.order[t] : t;
   };
   auto land = [&](int env) -> int {
@@ -650,17 +661,9 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   }
 #endif
   int env = land(resolve(draw()));
-#if OSC_TICKET_AHEAD == 2
-  int ticket = draw();
-#endif
+  unsigned ticket = draw();
   while (env < a.n_envs) {
-#if OSC_TICKET_AHEAD == 2
-    int drawn = resolve(ticket);
-    ticket = draw();
-#else
-    const int ticket = draw();
-    int drawn = 0;
-#endif
+    const int drawn = resolve(ticket);
     mbar_wait(bar, parity);
     parity ^= 1;
     const int lane0 = lane;
@@ -670,18 +673,13 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
     double* sx = a.sol_x + (size_t)env * D::N;
     double* sy = a.sol_y + (size_t)env * D::M;
     double* so = a.state + (size_t)env * D::STATE;
-#if OSC_TICKET_AHEAD == 2
     const typename C3::Prepared pr = C3::step_prepare(w, p, L, lane, sx, sy, so);
-#else
-    const typename C3::Prepared pr =
-        C3::step_prepare(w, p, L, lane, sx, sy, so, [&]() { drawn = resolve(ticket); });
-#endif
     __syncwarp();
     OSC_TICK(1);
     const int next = land(drawn);
     OSC_TICK(2);
-    const Result r =
-        C3::step_solve(w, p, L, lane, pr, sx, sy, a.torque + (size_t)env * D::NU, so);
+    const Result r = C3::step_solve(w, p, L, lane, pr, sx, sy, a.torque + (size_t)env * D::NU,
+                                    so, [&]() { ticket = draw(); });
     if (lane == 0) {
       a.iters[env] = r.iter;
       a.status[env] = r.status;
@@ -1291,7 +1289,7 @@ int launch_solve3w(osc_handle* h, cudaStream_t st, int env0, int n, int counter)
   a.n_envs = n;
   kern<<<grid, WARPS * 32, smem, st>>>(h->params, a);
   OSC_CUDA(h, cudaGetLastError());
-  h->ctr_base[counter] += (unsigned)n + (unsigned)OSC_TICKET_AHEAD * (unsigned)(grid * WARPS);
+  h->ctr_base[counter] += (unsigned)n + 2u * (unsigned)(grid * WARPS);
   h->launches++;
   return OSC_OK;
 }
