@@ -220,9 +220,10 @@ int osc_host_free(void *p);
 /* Per-kernel device timing: when enabled, every osc_step brackets its kernels with CUDA
  * events on the launch stream; osc_timing_read synchronises, returns the average
  * milliseconds per step of each kernel since the last read, and resets.
- * build = objective build (H, f); scale = OSQP scale_data (Ruiz equilibration; 0 for robots
- * on the generic solver core, which scales inside the solve kernel); solve = assembly,
- * factorisation, ADMM, un-scaling. */
+ * scale = the fused objective-build + equilibration kernel (H, f, OSQP scale_data); solve =
+ * assembly, factorisation, ADMM, un-scaling; build = the gap between the step's first event
+ * and the fused kernel (a few microseconds) -- or, after osc_set_fused_build(h, 0) and in
+ * osc_step_condensed, the stand-alone objective-build kernel, with scale = equilibration alone. */
 typedef struct {
   float build_ms, solve_ms;
   int steps;
