@@ -606,7 +606,13 @@ solve_kernel3(const __grid_constant__ Params p, const SolveArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WS* wsb = reinterpret_cast<WS*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WARPS * sizeof(WS));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (opaque: under register pressure the compiler otherwise re-derives the workspace address
+  // from %tid inside the iteration loop -- four S2R per iteration on the Go2 shape)
+  // (one lane per row only: the two-lane shape keeps the address in a register by itself and
+  // loses seven instructions per iteration to moves with the opaque ids)
+  constexpr bool kOpaqueIds = 2 * D::NV > 32;
+  const int warp = kOpaqueIds ? osc_opaque((int)(threadIdx.x >> 5)) : (int)(threadIdx.x >> 5);
+  const int lane = kOpaqueIds ? osc_opaque((int)(threadIdx.x & 31)) : (int)(threadIdx.x & 31);
   WS& w = wsb[warp];
   uint64_t* bar = &bars[warp];
   if (lane == 0) {
