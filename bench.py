@@ -631,6 +631,43 @@ def main():
     # bytes the C-ABI actually moved per step (it skips Jacobian rows nothing reads)
     e2e_h2d, e2e_d2h = osc.host_traffic()
 
+    # ---- the same end-to-end step with the task Jacobian handed over in FP32 (opt-in
+    #      osc_step_host_j32: widened on the device, FP64 from there on) -- reported separately
+    #      with what the rounding of J does to the answer on this workload
+    j32_sets = []
+    for t in range(NSETS):
+        a = capi.pinned_empty(host_sets[t]["J"].shape, np.float32)
+        a[...] = host_sets[t]["J"]
+        j32_sets.append(a)
+    ptrs32 = [list(p) for p in ptrs]
+    for t in range(NSETS):
+        ptrs32[t][FIELDS.index("J")] = j32_sets[t].ctypes.data
+    tq64 = tq.copy()  # torques of the last FP64-transport step (tick warmup + steps - 1)
+    tq32 = capi.pinned_empty((n_envs, spec.nu))
+    osc.setup(host_sets[0], stream)
+    for t in range(args.warmup):
+        osc.step_host_j32_into(ptrs32[t % NSETS], tq32, stream)
+    barrier()
+    j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    j0.record()
+    for t in range(args.warmup, args.warmup + args.steps):
+        osc.step_host_j32_into(ptrs32[t % NSETS], tq32, stream)
+    j1.record()
+    barrier()
+    j32_ms = sharding.max_over_ranks(j0.elapsed_time(j1) / args.steps, dev)
+    j32_h2d, _ = osc.host_traffic()
+    dj = np.abs(tq32 - tq64)
+    tolj = 1e-5 + 1e-4 * np.abs(tq64)
+    e2e_j32 = {"value": world * n_envs / (j32_ms * 1e-3), "unit": UNIT, "ms_per_step": j32_ms,
+               "h2d_bytes_per_step": j32_h2d, "d2h_bytes_per_step": e2e_d2h,
+               "pcie_h2d_gbs": j32_h2d / (j32_ms * 1e-3) / 1e9,
+               "torques_within_tol_of_fp64_transport": float((dj <= tolj).all(1).mean()),
+               "worst_dtau_over_tol": float((dj / tolj).max()),
+               "note": "opt-in osc_step_host_j32: J in FP32 over the host link, FP64 on the device; "
+                       "same ticks as the e2e leg, compared after the same number of warm steps "
+                       "(rank 0's environments)"}
+    del j32_sets
+
     # ---- the all-gather of torques + statistics as peer stores behind the
     #      C-ABI (osc_gather_*): timed alone, and inside a second timed loop of resident
     #      steps so that `value_incl_gather` is measured, not derived
@@ -819,6 +856,7 @@ def main():
                     "limit": "PCIe: the OSCData record (M, J, bias, ...) is 13.4 kB per environment "
                              "and crosses the host link every step; at N > 1 ranks that share a "
                              "PCIe switch / socket share its bandwidth (see per-rank rates)"},
+            "e2e_fp32_jacobian": e2e_j32,
             "gpu_launches": int(stats["launches"]),
             "roofline": roofline, "roofline_scale": roofline_scale,
             "roofline_build": roofline_build, "three_kernel_form": three_kernel_form,

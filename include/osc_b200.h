@@ -176,6 +176,17 @@ int osc_step_host(osc_handle *h, const double *M, const double *C, const double 
                   const double *bias, const double *targets, const double *mask, double *torque,
                   void *stream);
 
+/* osc_step_host with the task Jacobian handed over in FP32 (opt-in: a producer that already
+ * holds J in single precision -- MuJoCo built with mjUSESINGLE, an FP32 simulator -- halves the
+ * 77 % of the host-link bytes that are J).  The rows are widened to FP64 on the device
+ * (widen_rows_kernel) and EVERYTHING downstream stays FP64: with J values that are exactly
+ * representable in FP32 the results are those of osc_step_host bit for bit; otherwise the QP
+ * data differ by the rounding of J (relative 6e-8), measured against the parity gate in
+ * tests/test_gpu_parity.py and reported separately by bench.py, never the headline path. */
+int osc_step_host_j32(osc_handle *h, const double *M, const double *C, const float *J32,
+                      const double *bias, const double *targets, const double *mask,
+                      double *torque, void *stream);
+
 /* Self-test of the warp primitives the register-resident solver core is written against
  * (csrc/osc_warp.cuh): runs the shuffles, the 16-way transposing max, the warp sum and one FP64
  * tensor-core tile product on `in` ([18][32] doubles: rows 0-15 non-negative values, row 16 an

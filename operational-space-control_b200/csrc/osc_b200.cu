@@ -953,6 +953,19 @@ struct GatherArgs {
   double step;
 };
 
+// FP32 transport of the task Jacobian (opt-in, osc_step_host_j32): rows [r0, r1) of every
+// environment of a chunk, float -> double, into the FP64 input buffer the kernels read.
+__global__ void __launch_bounds__(256)
+widen_rows_kernel(const float* __restrict__ src, double* __restrict__ dst, int n_envs,
+                  int row_elems /* s * nv */, int off /* r0 * nv */, int len /* (r1 - r0) * nv */) {
+  const size_t total = (size_t)n_envs * len;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i / len, k = i - e * len;
+    dst[e * row_elems + off + k] = (double)src[e * row_elems + off + k];
+  }
+}
+
 constexpr int kGatherThreads = 1024;
 __global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const __grid_constant__ GatherArgs a) {
   if (blockIdx.x == 0) {
@@ -1104,6 +1117,7 @@ struct osc_handle {
   bool kernels_ready;   // function attributes of the scale / solve kernels are set
   bool build_ready;     // ... of the build kernel (+ its resident grid size)
   bool cond_ready;      // ... of the condensed kernel
+  float* dJ32;          // FP32 landing buffer of the task Jacobian (osc_step_host_j32), lazily allocated
   bool fused_ready;     // ... of the fused build + equilibration kernel
   bool scale_ready;     // ... of the stand-alone equilibration kernel
   bool fuse_build;      // osc_step runs build_scale_kernel3 instead of build + scale (default)
@@ -1521,6 +1535,7 @@ int osc_create(const osc_robot_spec* spec, const osc_settings* settings, int n_e
   h->kernels_ready = false;
   h->build_ready = false;
   h->cond_ready = false;
+  h->dJ32 = nullptr;
   h->fused_ready = false;
   h->scale_ready = false;
   h->fuse_build = true;
@@ -1540,6 +1555,7 @@ int osc_destroy(osc_handle* h) {
     if (h->g_ipc_opened[p] && h->g_peer[p]) cudaIpcCloseMemHandle(h->g_peer[p]);
   if (h->g_slab) cudaFree(h->g_slab);
   if (h->dStateC) cudaFree(h->dStateC);
+  if (h->dJ32) cudaFree(h->dJ32);
   if (h->hIn) cudaFreeHost(h->hIn);
   if (h->hTq) cudaFreeHost(h->hTq);
   if (h->dIters) cudaFree(h->dIters);
@@ -1829,8 +1845,8 @@ int osc_sync(osc_handle* h, void* stream) {
 // is what such a step's latency consists of.
 constexpr size_t kFewRobotsBytes = 128 * 1024;
 static int step_host_few(osc_handle* h, const double* M, const double* C, const double* J,
-                         const double* bias, const double* targets, const double* mask,
-                         double* torque, cudaStream_t st) {
+                         const float* J32, const double* bias, const double* targets,
+                         const double* mask, double* torque, cudaStream_t st) {
   const size_t B = sizeof(double), N = (size_t)h->n_envs;
   const size_t nv = h->nv, s = h->s, nc = h->nc, nu = h->nu;
   if (!h->hIn) {
@@ -1841,9 +1857,14 @@ static int step_host_few(osc_handle* h, const double* M, const double* C, const 
   std::memcpy(h->hIn + h->in_off[0], M, N * nv * nv * B);
   std::memcpy(h->hIn + h->in_off[1], C, N * nv * B);
   for (size_t e = 0; e < N; ++e)  // only the rows the kernels read leave the caller's buffer
-    for (const auto& r : h->j_rows)
-      std::memcpy(h->hIn + h->in_off[2] + (e * s + (size_t)r.first) * nv,
-                  J + (e * s + (size_t)r.first) * nv, (size_t)(r.second - r.first) * nv * B);
+    for (const auto& r : h->j_rows) {
+      const size_t off = (e * s + (size_t)r.first) * nv, len = (size_t)(r.second - r.first) * nv;
+      if (J32) {  // (a few robots: widened while staging)
+        for (size_t k = 0; k < len; ++k) h->hIn[h->in_off[2] + off + k] = (double)J32[off + k];
+      } else {
+        std::memcpy(h->hIn + h->in_off[2] + off, J + off, len * B);
+      }
+    }
   std::memcpy(h->hIn + h->in_off[3], bias, N * s * B);
   std::memcpy(h->hIn + h->in_off[4], targets, N * s * B);
   std::memcpy(h->hIn + h->in_off[5], mask, N * nc * B);
@@ -1863,15 +1884,15 @@ static int step_host_few(osc_handle* h, const double* M, const double* C, const 
   return OSC_OK;
 }
 
-int osc_step_host(osc_handle* h, const double* M, const double* C, const double* J,
-                  const double* bias, const double* targets, const double* mask, double* torque,
-                  void* stream) {
+static int step_host_impl(osc_handle* h, const double* M, const double* C, const double* J,
+                          const float* J32, const double* bias, const double* targets,
+                          const double* mask, double* torque, void* stream) {
   if (check_handle(h)) return OSC_ERR_INVALID;
   if (!h->setup_done) {
     h->err = "osc_step_host: osc_setup has not been called";
     return OSC_ERR_STATE;
   }
-  if (!M || !C || !J || !bias || !targets || !mask || !torque) {
+  if (!M || !C || (!J && !J32) || !bias || !targets || !mask || !torque) {
     h->err = "osc_step_host: null host buffer";
     return OSC_ERR_INVALID;
   }
@@ -1882,7 +1903,13 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
   }
   cudaStream_t st = (cudaStream_t)stream;
   OSC_CUDA(h, cudaSetDevice(h->device));
-  if (h->in_doubles * sizeof(double) <= kFewRobotsBytes) return step_host_few(h, M, C, J, bias, targets, mask, torque, st);
+  if (h->in_doubles * sizeof(double) <= kFewRobotsBytes)
+    return step_host_few(h, M, C, J, J32, bias, targets, mask, torque, st);
+  if (J32 && !h->dJ32) {  // FP32 landing buffer; rows that are never uploaded stay zero
+    const size_t bytes = (size_t)h->n_envs * h->s * h->nv * sizeof(float);
+    OSC_CUDA(h, cudaMalloc((void**)&h->dJ32, bytes));
+    OSC_CUDA(h, cudaMemset(h->dJ32, 0, bytes));
+  }
   // Software pipeline over chunks of environments: the H2D copy of chunk c+1 (copy stream)
   // overlaps build+solve of chunk c (caller's stream); torques return per chunk.
   const int N = h->n_envs;
@@ -1907,7 +1934,15 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
     const size_t n = (size_t)((e0 + chunk <= (size_t)N) ? chunk : N - e0);
     cudaStream_t cs = h->copy_stream;
     // task Jacobian: only the rows the kernels read (zero-weight task rows stay behind)
-    if (h->j_rows.size() == 1 && h->j_rows[0].first == 0 && h->j_rows[0].second == (int)s) {
+    if (J32) {
+      const size_t F = sizeof(float);
+      for (const auto& r : h->j_rows) {
+        const size_t off = e0 * s * nv + (size_t)r.first * nv;
+        OSC_CUDA(h, cudaMemcpy2DAsync(h->dJ32 + off, s * nv * F, J32 + off, s * nv * F,
+                                      (size_t)(r.second - r.first) * nv * F, n,
+                                      cudaMemcpyHostToDevice, cs));
+      }
+    } else if (h->j_rows.size() == 1 && h->j_rows[0].first == 0 && h->j_rows[0].second == (int)s) {
       OSC_CUDA(h, cudaMemcpyAsync(h->dJ + e0 * s * nv, J + e0 * s * nv, n * s * nv * B, cudaMemcpyHostToDevice, cs));
     } else {
       for (const auto& r : h->j_rows) {
@@ -1924,6 +1959,17 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
     OSC_CUDA(h, cudaMemcpyAsync(h->dMask + e0 * nc, mask + e0 * nc, n * nc * B, cudaMemcpyHostToDevice, cs));
     OSC_CUDA(h, cudaEventRecord(h->chunk_ev[c], cs));
     OSC_CUDA(h, cudaStreamWaitEvent(st, h->chunk_ev[c], 0));
+    if (J32) {  // widen on the compute stream: the copy stream keeps the link busy meanwhile
+      for (const auto& r : h->j_rows) {
+        const int len = (r.second - r.first) * (int)nv;
+        int grid = (int)((n * len + 255) / 256);
+        if (grid > h->sm_count * 8) grid = h->sm_count * 8;
+        osc::widen_rows_kernel<<<grid, 256, 0, st>>>(h->dJ32 + e0 * s * nv, h->dJ + e0 * s * nv,
+                                                     (int)n, (int)(s * nv), r.first * (int)nv, len);
+        OSC_CUDA(h, cudaGetLastError());
+        h->launches++;
+      }
+    }
     int rc = h->fuse_build ? OSC_OK : OSC_DISPATCH(h, launch_build, h, st, (int)e0, (int)n);
     if (rc) return rc;
     h->fuse_now = h->fuse_build;
@@ -1936,11 +1982,28 @@ int osc_step_host(osc_handle* h, const double* M, const double* C, const double*
   {
     size_t jrows = 0;
     for (const auto& r : h->j_rows) jrows += (size_t)(r.second - r.first);
-    h->host_h2d_bytes = (size_t)N * B * (jrows * nv + nv * nv + 2 * s + nv + nc);
+    h->host_h2d_bytes = (size_t)N * B * (nv * nv + 2 * s + nv + nc) +
+                        (size_t)N * jrows * nv * (J32 ? sizeof(float) : B);
     h->host_d2h_bytes = (size_t)N * B * nu;
   }
   OSC_CUDA(h, cudaStreamSynchronize(st));
   return OSC_OK;
+}
+
+int osc_step_host(osc_handle* h, const double* M, const double* C, const double* J,
+                  const double* bias, const double* targets, const double* mask, double* torque,
+                  void* stream) {
+  return step_host_impl(h, M, C, J, nullptr, bias, targets, mask, torque, stream);
+}
+
+int osc_step_host_j32(osc_handle* h, const double* M, const double* C, const float* J32,
+                      const double* bias, const double* targets, const double* mask,
+                      double* torque, void* stream) {
+  if (!J32) {
+    if (h) h->err = "osc_step_host_j32: null host buffer";
+    return OSC_ERR_INVALID;
+  }
+  return step_host_impl(h, M, C, nullptr, J32, bias, targets, mask, torque, stream);
 }
 
 #ifdef OSC_PHASE_CLOCKS

@@ -32,7 +32,7 @@ EXPORTS = (
     "osc_gather_create", "osc_gather_attach", "osc_gather_torques", "osc_gather_buffers",
     "osc_step_condensed", "osc_reset_condensed", "osc_kinematics",
     "osc_walter_tumbling_default_gains", "osc_targets_walter_tumbling",
-    "osc_set_fused_build",
+    "osc_set_fused_build", "osc_step_host_j32",
 )
 KIN_MAX_BODIES = 16
 IPC_HANDLE_BYTES = 64
@@ -159,6 +159,8 @@ def load():
     L.osc_reinit_count.argtypes = [vp, ip, vp]
     L.osc_download_objective.argtypes = [vp, vp, vp, vp]
     L.osc_step_host.argtypes = [vp] + [vp] * 7 + [vp]
+    L.osc_step_host_j32.argtypes = [vp] + [vp] * 7 + [vp]
+    L.osc_set_fused_build.argtypes = [vp, C.c_int]
     L.osc_kernel_launches.argtypes = [vp]
     L.osc_kernel_launches.restype = C.c_longlong
     L.osc_measure_dfma_tflops.argtypes = [C.c_int, dp]
@@ -310,6 +312,12 @@ class BatchedOSC:
         """Hot-loop variant of step(): pre-resolved input pointers, caller-owned output."""
         self._check(self.L.osc_step_host(self.h, *ptrs, torque_out.ctypes.data, stream),
                     "osc_step_host")
+
+    def step_host_j32_into(self, ptrs, torque_out: np.ndarray, stream=None):
+        """step_host_into with the task Jacobian in FP32 (ptrs[2] points at float32 data of the
+        same [n_envs, s, nv] shape): opt-in FP32 transport of J, widened on the device."""
+        self._check(self.L.osc_step_host_j32(self.h, *ptrs, torque_out.ctypes.data, stream),
+                    "osc_step_host_j32")
 
     def kinematics(self, model: CKinModel, qpos_dev: int, qvel_dev: int, stream=None):
         """M, C, J, bias of every environment from qpos / qvel (DEVICE pointers) into the

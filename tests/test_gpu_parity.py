@@ -1117,3 +1117,52 @@ def test_long_horizon_parity_at_batch_scale(oracle):
     print(f"batch-scale horizon: {n_envs} envs x {T} ticks, worst |dtau|/tol {worst_repro:.3g} where "
           f"the oracle variants agree, {worst_any:.3g} against the nearer variant elsewhere "
           f"({n_part} environment-steps on which they part), longest solve {iters_max} iterations")
+
+
+@pytest.mark.parametrize("preset,config,n_envs", [("walter_sr_true_tumbling_mjjoint", "tumbling", 4096),
+                                                  ("unitree_go2", "go2_standing", 3)])
+def test_fp32_transport_of_the_task_jacobian(oracle, preset, config, n_envs):
+    """osc_step_host_j32 (opt-in): J crosses the host link in FP32 and is widened on the
+    device; everything downstream stays FP64.
+    (1) The transport itself is exact: with J values that FP32 represents exactly, cold + warm
+        steps give the results of osc_step_host on the same values bit for bit (chunked
+        pipeline at 4096 environments, few-robot route at 3).
+    (2) What rounding J to FP32 does to the answer (test, do not assume): against the oracle
+        on the UNROUNDED data, iteration counts and the torque gate are reported and must hold
+        for the bulk of the environments; this is why the mode is opt-in and reported
+        separately, never the gated path."""
+    import osc_b200 as ob
+    from osc_b200 import capi
+    spec = ob.load_preset(preset)
+    F = ("M", "C", "J", "bias", "targets", "mask")
+    steps = [ob.synth.make_inputs(spec, n_envs, config, step=t) for t in range(3)]
+    j32 = [np.ascontiguousarray(s["J"].astype(np.float32)) for s in steps]
+    rounded = [dict(s, J=j.astype(np.float64)) for s, j in zip(steps, j32)]
+    g64 = capi.BatchedOSC(spec, n_envs)
+    g32 = capi.BatchedOSC(spec, n_envs)
+    g64.setup(rounded[0])
+    g32.setup(rounded[0])
+    b = oracle.OracleBatch(spec, n_envs, oracle.default_settings())
+    b.setup(steps[0])
+    tq = np.empty((n_envs, spec.nu))
+    for t in range(3):
+        a = g64.step(rounded[t])
+        ra = g64.results()
+        ptrs = [rounded[t][k].ctypes.data for k in F]
+        ptrs[2] = j32[t].ctypes.data
+        g32.step_host_j32_into(ptrs, tq)
+        rb = g32.results()
+        assert np.array_equal(a, tq) and np.array_equal(ra["iters"], rb["iters"]), t
+        assert np.array_equal(ra["x"], rb["x"], equal_nan=True), t
+        h2d, _ = g32.host_traffic()
+        h2d64, _ = g64.host_traffic()
+        if n_envs > 64:
+            assert h2d < 0.65 * h2d64, (h2d, h2d64)
+        o = b.step(steps[t])
+        same = rb["iters"] == o["iters"]
+        d = np.abs(tq - o["torque"])
+        tol = ATOL + RTOL * np.abs(o["torque"])
+        ok = (d <= tol).all(1)
+        print(f"FP32 J {preset} step {t}: iterations equal {same.mean():.4f}, within tol {ok.mean():.4f}, "
+              f"worst |dtau|/tol {(d / tol).max():.3g}, H2D bytes {h2d / h2d64:.3f} of the FP64 route")
+        assert same.mean() >= 0.9 and ok.mean() >= 0.9, (t, same.mean(), ok.mean())
