@@ -7,20 +7,31 @@
 //                     pulled into shared memory by 1-D TMA bulk copies (cp.async.bulk,
 //                     mbarrier completion) through a 2-stage ring per warp; the products
 //                     J'WJ and J'W(bias - t) run on the FP64 tensor cores (DMMA).
+//                     Stand-alone form: osc_setup, the condensed mode, the three-kernel step.
 //   init_state_kernel set_up_optimization(): cold iterates, rho0, first linear cost.
-//   scale_kernel3     K3a: OSQP's scale_data (Ruiz equilibration + cost scaling) and the
+//   build_scale_kernel3
+//                     K2 + K3a fused (the default first kernel of a control step): the warp
+//                     lands M, J, bias, targets, builds H and f in shared memory (DMMA), sends
+//                     them out with bulk stores and runs the Ruiz passes on registers.
+//   scale_kernel3     K3a alone: OSQP's scale_data (Ruiz equilibration + cost scaling) and the
 //                     update-path decision, one warp per environment, unscaled matrices in
 //                     registers for all passes (osc::Core3::ruiz).
 //   solve_kernel3     K3b: one warp per environment, persistent CTAs with a dynamic work
 //                     counter and a per-warp landing stage (the next environment's TMA bulk
 //                     copies overlap the solve of the current one): assembly, factorisation,
-//                     ADMM with register-resident matrices, un-scaling, entirely on chip in
-//                     FP64 (osc::Core3::step_prepare / step_solve).
+//                     ADMM with register-resident matrices (two exchanges per iteration),
+//                     un-scaling, entirely on chip in FP64 (osc::Core3::step_prepare /
+//                     step_solve).
+//   condensed_kernel  K1 + K3 of the condensed fast mode (osc_condensed.cuh), reported separately.
+//   kinematics_kernel M, C, J, Jdot qvel of a floating-base hinge tree (osc_kinematics.cuh).
 //   order_kernel      longest-first hand-out order of solve_kernel3's work counter (scheduling).
 //   reset_warm_kernel reset_optimization().
-//   targets_pd_kernel, contact_mask_kernel
-//                     the step before the path for device-resident roll-outs: task-space PD
+//   targets_pd_kernel, targets_walter_tumbling_kernel, contact_mask_kernel
+//                     the step before the path for device-resident roll-outs: task-space
 //                     targets and contact masks.
+//   widen_rows_kernel FP32 -> FP64 rows of J (opt-in FP32 transport, osc_step_host_j32).
+//   gather_push_kernel
+//                     torques + statistics of a rank into every rank's slab (peer stores).
 //   warp_selftest_kernel
 //                     the device reading of the warp primitives of osc_warp.cuh (tests).
 //   dfma_peak_kernel  FP64-FMA roofline denominator.
