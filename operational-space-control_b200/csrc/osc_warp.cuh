@@ -73,49 +73,27 @@ struct Warp {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
   }
-  static OSC_HD double max(const Var<double>& a) {  // non-negative, non-NaN values
-    double v = a.v;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double t = __shfl_xor_sync(kFull, v, o);
-      v = t > v ? t : v;
-    }
-    return v;
+  // Maximum of NON-NEGATIVE values (a NaN never becomes the maximum, like OSQP's
+  // vec_norm_inf): for non-negative doubles the numeric order is the unsigned order of the
+  // (high word, low word) pair, so two integer warp reductions (REDUX) replace five rounds of
+  // 64-bit shuffle + compare + select.
+  static OSC_HD double max(const Var<double>& a) {
+    const double v = a.v == a.v ? a.v : 0.0;
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned himax = __reduce_max_sync(kFull, hi);
+    const unsigned lomax = __reduce_max_sync(kFull, hi == himax ? lo : 0u);
+    return __hiloint2double((int)himax, (int)lomax);
   }
   static OSC_HD unsigned ballot(const Var<bool>& p) { return __ballot_sync(kFull, p.v); }
-  // Warp-wide maxima of NQ (8 or 16) non-negative quantities at once: a transposing butterfly
-  // (every level halves the number of quantities a lane carries: 8+4+2+1+1 = 16 shuffles for
-  // 16 quantities instead of 16 x 5, 4+2+1+1+1 = 9 for 8), after which lane l holds quantity
-  // l / (32 / NQ); the results go through `scratch` (NQ doubles of shared memory) to `out`,
-  // which every lane receives.
+  // Warp-wide maxima of NQ non-negative quantities; every lane receives all of them.  Two
+  // integer warp reductions per quantity (see max()); `scratch` is unused on the device (the
+  // results arrive in uniform registers), the host emulation keeps the interface.
   template <int NQ>
   static OSC_HD void maxn(Var<double> (&m)[NQ], double* out, double* scratch, int lane) {
-    static_assert(NQ == 8 || NQ == 16, "quantities per reduction");
-    constexpr int G = 32 / NQ;  // lanes that end up with the same quantity
-    double v[NQ];
+    (void)scratch;
+    (void)lane;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) v[q] = m[q].v;
-#pragma unroll
-    for (int h = NQ / 2; h >= 1; h >>= 1) {  // h = quantities kept; partner offset = G h
-      const bool up = (lane & (G * h)) != 0;
-#pragma unroll
-      for (int q = 0; q < h; ++q) {
-        const double keep = up ? v[q + h] : v[q];
-        const double send = up ? v[q] : v[q + h];
-        const double t = __shfl_xor_sync(kFull, send, G * h);
-        v[q] = t > keep ? t : keep;
-      }
-    }
-#pragma unroll
-    for (int o = G / 2; o >= 1; o >>= 1) {
-      const double t = __shfl_xor_sync(kFull, v[0], o);
-      v[0] = t > v[0] ? t : v[0];
-    }
-    __syncwarp();
-    if (!(lane & (G - 1))) scratch[lane / G] = v[0];
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) out[q] = scratch[q];
+    for (int q = 0; q < NQ; ++q) out[q] = max(m[q]);
   }
   static OSC_HD void max16(Var<double> (&m)[16], double* out, double* scratch, int lane) {
     maxn<16>(m, out, scratch, lane);
@@ -169,9 +147,9 @@ struct Warp {
     }
     return v[0];
   }
-  static double max(const Var<double>& a) {
-    double m = a.v[0];
-    for (int l = 1; l < 32; ++l) m = a.v[l] > m ? a.v[l] : m;
+  static double max(const Var<double>& a) {  // non-negative values; a NaN never wins
+    double m = 0.0;
+    for (int l = 0; l < 32; ++l) m = a.v[l] > m ? a.v[l] : m;
     return m;
   }
   static unsigned ballot(const Var<bool>& p) {
@@ -182,11 +160,7 @@ struct Warp {
   }
   template <int NQ>
   static void maxn(Var<double> (&m)[NQ], double* out, double* scratch, int) {
-    for (int q = 0; q < NQ; ++q) {
-      double v = m[q].v[0];
-      for (int l = 1; l < 32; ++l) v = m[q].v[l] > v ? m[q].v[l] : v;
-      out[q] = scratch[q] = v;
-    }
+    for (int q = 0; q < NQ; ++q) out[q] = scratch[q] = max(m[q]);
   }
   static void max16(Var<double> (&m)[16], double* out, double* scratch, int) {
     maxn<16>(m, out, scratch, 0);
